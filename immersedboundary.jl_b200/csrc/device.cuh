@@ -1,0 +1,91 @@
+// Device-side internals shared by the CUDA translation units of libibx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <unordered_map>
+#include <mutex>
+#include "ibx_internal.h"
+
+struct ibx_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t comm_stream = nullptr;  // halo exchange / copies
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_ready = nullptr;
+  int64_t launches = 0;
+  bool poisoned = false;
+  struct Arr { float* p; int64_t rows, cols; };
+  std::unordered_map<int64_t, Arr> arrays;
+  int64_t next_handle = 1;
+  std::mutex mu;
+  // scratch for reductions
+  double* d_red = nullptr;
+  double* h_red = nullptr;  // pinned
+  int64_t red_cap = 0;
+  // scratch for fused kernels (ghost staging etc.)
+  float* d_scratch = nullptr;
+  int64_t scratch_cap = 0;
+  // end-to-end staging arrays
+  ibx_array e2e_Q = 0, e2e_R = 0, e2e_cfl = 0;
+  // NCCL
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+namespace ibx {
+
+int cuda_fail(ibx_ctx* c, cudaError_t e, const char* what, const char* file, int line);
+ibx_domain* find_domain(const ibx_domain* d);
+ibx_accum* find_accum(const ibx_accum* a);
+bool get_array(ibx_ctx* c, ibx_array h, ibx_ctx::Arr& out);
+float* ensure_scratch(ibx_ctx* c, int64_t nfloats);
+
+#define CU(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) return ibx::cuda_fail(c, e_, #call, __FILE__, __LINE__);   \
+  } while (0)
+
+#define CHECK_CTX(c)                                                                        \
+  do {                                                                                      \
+    if (!(c)) return ibx::fail(IBX_ERR_ARG, std::string(__func__) + ": null context");      \
+    if ((c)->poisoned) return ibx::fail(IBX_ERR_CUDA, "context poisoned by an earlier CUDA error"); \
+    cudaSetDevice((c)->device);                                                             \
+  } while (0)
+
+#define GET_ARR(var, h)                                                                              \
+  ibx_ctx::Arr var;                                                                                  \
+  if (!ibx::get_array(c, (h), var)) return ibx::fail(IBX_ERR_ARG, std::string(__func__) + ": invalid array handle " #h)
+
+#define GET_DOM(D, d)                                                                             \
+  ibx_domain* D##_p = ibx::find_domain(d);                                                        \
+  if (!D##_p) return ibx::fail(IBX_ERR_ARG, std::string(__func__) + ": unknown domain handle");   \
+  if (!D##_p->uploaded) return ibx::fail(IBX_ERR_STATE, std::string(__func__) + ": domain tables not uploaded (ibx_domain_upload)"); \
+  ibx_domain& D = *D##_p
+
+#define LAUNCH_CHECK()                                                           \
+  do {                                                                           \
+    c->launches++;                                                               \
+    cudaError_t e_ = cudaGetLastError();                                         \
+    if (e_ != cudaSuccess) return ibx::cuda_fail(c, e_, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+inline int grid_for(int64_t n, int block, int sm_count, int per_sm = 16) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)sm_count * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <class T>
+int upload_vec(ibx_ctx* c, const std::vector<T>& v, T** dptr) {
+  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  CU(cudaMalloc((void**)dptr, bytes));
+  if (!v.empty()) CU(cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return IBX_OK;
+}
+
+}  // namespace ibx

@@ -1,0 +1,268 @@
+// Host mesher: block octree refinement and cell enumeration.
+// Mirrors src/mesher.jl:811-1112 of the reference (refine_octree, refine_orderly, Mesh, get_cells).
+#include "ibx_internal.h"
+
+#include <numeric>
+
+namespace ibx {
+Num region_distance(const ibx_region& r, int nd, const double* x, bool xf32);
+std::shared_ptr<ibx_stl> refine_to_length_impl(const ibx_stl& s, Num h, double tol, bool tol_f32, double growth_ratio,
+                                               int nreg, const ibx_region* regs);
+std::shared_ptr<ibx_dfield> make_dfield(std::shared_ptr<ibx_stl> stl);
+std::shared_ptr<ibx_stl> lookup_stl(const ibx_stl* s);
+std::shared_ptr<ibx_dfield> lookup_dfield(const ibx_dfield* d);
+ibx_dfield* register_dfield(std::shared_ptr<ibx_dfield> d);
+
+static std::map<const ibx_mesh*, std::shared_ptr<ibx_mesh>> g_mesh;
+std::shared_ptr<ibx_mesh> lookup_mesh(const ibx_mesh* m) {
+  auto it = g_mesh.find(m);
+  if (it == g_mesh.end()) throw std::runtime_error("unknown ibx_mesh handle");
+  return it->second;
+}
+
+struct Criterion {
+  ibx_region region;
+  Num h;
+};
+
+// refine_octree (src/mesher.jl:811-862): depth-first, children in Iterators.product order (first dim fastest)
+static void refine_octree(const std::vector<Criterion>& crit, int nd, const float* origin, const float* widths,
+                          double gm1, std::vector<float>& out_o, std::vector<float>& out_w) {
+  struct Item {
+    float o[3], w[3];
+    std::vector<int> active;  // indices into crit
+  };
+  std::vector<Item> stack;
+  Item root;
+  for (int d = 0; d < nd; ++d) { root.o[d] = origin[d]; root.w[d] = widths[d]; }
+  root.active.resize(crit.size());
+  std::iota(root.active.begin(), root.active.end(), 0);
+  stack.push_back(std::move(root));
+  while (!stack.empty()) {
+    Item it = std::move(stack.back());
+    stack.pop_back();
+    float L = it.w[0], wmin = it.w[0];
+    double ss = 0;
+    for (int d = 0; d < nd; ++d) {
+      L = std::max(L, it.w[d]);
+      wmin = std::min(wmin, it.w[d]);
+      ss += (double)it.w[d] * (double)it.w[d];
+    }
+    float R = (float)std::sqrt(ss) / 2.0f;  // norm(widths) / 2, circumradius
+    double c[3];
+    for (int d = 0; d < nd; ++d) c[d] = (double)(float)(it.o[d] + it.w[d] / 2.0f);
+    std::vector<int> active;
+    for (int ci : it.active) {
+      Num dist = region_distance(crit[ci].region, nd, c, true);
+      Num lmax = nmax(nmul(Num{gm1, false}, nsub(dist, Num{(double)R, true})), crit[ci].h);
+      if (lmax.v < (double)L) active.push_back(ci);
+    }
+    if (active.empty()) {
+      for (int d = 0; d < nd; ++d) { out_o.push_back(it.o[d]); out_w.push_back(it.w[d]); }
+      continue;
+    }
+    int split[3] = {1, 1, 1};
+    float nw[3];
+    std::vector<float> axes[3];
+    for (int d = 0; d < nd; ++d) {
+      split[d] = (int)std::nearbyint((double)(it.w[d] / wmin)) + 1;
+      nw[d] = it.w[d] / (float)split[d];
+      double a = (double)it.o[d], b = (double)(float)(it.o[d] + it.w[d]);
+      for (int s = 0; s < split[d]; ++s) {
+        double t = (double)s / (double)split[d];
+        axes[d].push_back((float)((1.0 - t) * a + t * b));  // LinRange lerp (Base.lerpi)
+      }
+    }
+    int total = split[0] * split[1] * split[2];
+    // push in reverse so that children pop in product order
+    for (int idx = total - 1; idx >= 0; --idx) {
+      int i0 = idx % split[0], i1 = (idx / split[0]) % split[1], i2 = idx / (split[0] * split[1]);
+      int ii[3] = {i0, i1, i2};
+      Item ch;
+      for (int d = 0; d < nd; ++d) { ch.o[d] = axes[d][ii[d]]; ch.w[d] = nw[d]; }
+      ch.active = active;
+      stack.push_back(std::move(ch));
+    }
+  }
+}
+
+void mesh_cells(const ibx_mesh& m, float* centers, float* widths) {
+  // get_cells, margin = 0 (src/mesher.jl:1064-1112): block-major, first dim fastest in a block
+  int nd = m.nd, bs = m.block_size;
+  int64_t cpb = m.cells_per_block(), nb = m.nblocks();
+  std::vector<float> ic(bs);
+  for (int i = 0; i < bs; ++i) ic[i] = ((float)i + 0.5f) / (float)bs;
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < nb; ++b) {
+    const float* bo = &m.block_origins[b * nd];
+    const float* bw = &m.block_widths[b * nd];
+    float cw[3];
+    for (int d = 0; d < nd; ++d) cw[d] = bw[d] / (float)bs;
+    for (int64_t l = 0; l < cpb; ++l) {
+      int64_t rem = l;
+      for (int d = 0; d < nd; ++d) {
+        int i = (int)(rem % bs);
+        rem /= bs;
+        float prod = ic[i] * bw[d];
+        if (centers) centers[(b * cpb + l) * nd + d] = prod + bo[d];
+        if (widths) widths[(b * cpb + l) * nd + d] = cw[d];
+      }
+    }
+  }
+}
+
+}  // namespace ibx
+
+using namespace ibx;
+
+extern "C" {
+
+int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf, const ibx_surface* surfaces,
+                    int nregions, const ibx_region* regions, double growth_ratio, double tolerance, int tol_is_f32,
+                    int block_size, ibx_mesh** out) {
+  IBX_TRY
+  IBX_REQUIRE(nd == 2 || nd == 3, "nd must be 2 or 3");
+  IBX_REQUIRE(block_size >= 1, "block_size must be positive");
+  auto m = std::make_shared<ibx_mesh>();
+  m->nd = nd;
+  m->block_size = block_size;
+  for (int d = 0; d < nd; ++d) { m->origin[d] = origin[d]; m->widths[d] = widths[d]; }
+  // refine_orderly (src/mesher.jl:878-918): surfaces by increasing h; every refined surface becomes a
+  // refinement region (at h * ratio, ratio = 0.5f0) for the ones that follow
+  const float ratio = 0.5f;
+  auto scaled = [&](double h, bool f32, float fac) -> Num {
+    if (f32) return {(double)((float)h * fac), true};
+    return {h * (double)fac, false};
+  };
+  std::vector<ibx_region> regs;
+  for (int r = 0; r < nregions; ++r) {
+    ibx_region rr = regions[r];
+    if (rr.kind == 3) rr.dfield = lookup_dfield(rr.dfield).get();
+    Num hs = scaled(rr.h, rr.h_is_f32 != 0, ratio);
+    rr.h = hs.v;
+    rr.h_is_f32 = hs.f32;
+    regs.push_back(rr);
+  }
+  std::vector<int> order(nsurf);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return surfaces[a].h < surfaces[b].h; });
+  m->surf_names.resize(nsurf);
+  m->surf_fields.resize(nsurf);
+  for (int i : order) {
+    const ibx_surface& sf = surfaces[i];
+    Num h = scaled(sf.h, sf.h_is_f32 != 0, ratio);
+    std::shared_ptr<ibx_dfield> df;
+    if (sf.stl) {
+      auto stl = refine_to_length_impl(*lookup_stl(sf.stl), h, tolerance, tol_is_f32 != 0, growth_ratio,
+                                       (int)regs.size(), regs.data());
+      df = make_dfield(stl);
+    } else {
+      IBX_REQUIRE(nd == 3, "analytic sphere surfaces are 3-D only");
+      df = std::make_shared<ibx_dfield>();
+      df->sphere = true;
+      for (int d = 0; d < 3; ++d) df->sc[d] = sf.sphere_c[d];
+      df->sr = sf.sphere_r;
+    }
+    register_dfield(df);
+    m->surf_names[i] = sf.name ? sf.name : "";
+    m->surf_fields[i] = df;
+    ibx_region rr{};
+    rr.kind = 3;
+    rr.dfield = df.get();
+    rr.h = h.v;
+    rr.h_is_f32 = h.f32;
+    regs.push_back(rr);
+  }
+  // refinement criteria of the octree (src/mesher.jl:1013-1021): sizes times block_size
+  std::vector<Criterion> crit;
+  auto times_bs = [&](double h, bool f32) -> Num {
+    if (f32) return {(double)((float)h * (float)block_size), true};
+    return {h * (double)block_size, false};
+  };
+  for (int r = 0; r < nregions; ++r) {
+    Criterion c;
+    c.region = regions[r];
+    if (c.region.kind == 3) c.region.dfield = lookup_dfield(regions[r].dfield).get();
+    c.h = times_bs(regions[r].h, regions[r].h_is_f32 != 0);
+    crit.push_back(c);
+  }
+  for (int i = 0; i < nsurf; ++i) {
+    Criterion c;
+    c.region = ibx_region{};
+    c.region.kind = 3;
+    c.region.dfield = m->surf_fields[i].get();
+    c.h = times_bs(surfaces[i].h, surfaces[i].h_is_f32 != 0);
+    crit.push_back(c);
+  }
+  refine_octree(crit, nd, m->origin, m->widths, growth_ratio - 1.0, m->block_origins, m->block_widths);
+  g_mesh[m.get()] = m;
+  *out = m.get();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_from_blocks(const ibx_mesh* like, int block_size, ibx_mesh** out) {
+  IBX_TRY
+  auto src = lookup_mesh(like);
+  IBX_REQUIRE(block_size >= 1, "block_size must be positive");
+  auto m = std::make_shared<ibx_mesh>(*src);
+  m->block_size = block_size;
+  g_mesh[m.get()] = m;
+  *out = m.get();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_free(ibx_mesh* m) {
+  g_mesh.erase(m);
+  return IBX_OK;
+}
+
+int ibx_mesh_info(const ibx_mesh* mh, int* nd, int* block_size, int64_t* nblocks, int64_t* ncells, int* nsurf) {
+  IBX_TRY
+  auto m = lookup_mesh(mh);
+  *nd = m->nd;
+  *block_size = m->block_size;
+  *nblocks = m->nblocks();
+  *ncells = m->ncells();
+  *nsurf = (int)m->surf_names.size();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_blocks(const ibx_mesh* mh, float* block_origins, float* block_widths) {
+  IBX_TRY
+  auto m = lookup_mesh(mh);
+  std::copy(m->block_origins.begin(), m->block_origins.end(), block_origins);
+  std::copy(m->block_widths.begin(), m->block_widths.end(), block_widths);
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_surface_name(const ibx_mesh* mh, int i, const char** name) {
+  IBX_TRY
+  auto m = lookup_mesh(mh);
+  IBX_REQUIRE(i >= 0 && i < (int)m->surf_names.size(), "surface index out of range");
+  *name = m->surf_names[i].c_str();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_surface_dfield(const ibx_mesh* mh, int i, const ibx_dfield** out) {
+  IBX_TRY
+  auto m = lookup_mesh(mh);
+  IBX_REQUIRE(i >= 0 && i < (int)m->surf_fields.size(), "surface index out of range");
+  *out = m->surf_fields[i].get();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_cells(const ibx_mesh* mh, float* centers, float* widths) {
+  IBX_TRY
+  auto m = lookup_mesh(mh);
+  mesh_cells(*m, centers, widths);
+  return IBX_OK;
+  IBX_CATCH
+}
+
+}  // extern "C"

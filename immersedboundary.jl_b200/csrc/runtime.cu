@@ -1,0 +1,317 @@
+// Device runtime of libibx.so: context, opaque float32 arrays, one-time upload of the Domain tables.
+// The upload replaces the reference's per-call `to_backend(part, conv_to_backend)`
+// (src/ImmersedBoundary.jl:846-849, src/arraybends.jl:14-77).
+#include "device.cuh"
+
+namespace ibx {
+
+int cuda_fail(ibx_ctx* c, cudaError_t e, const char* what, const char* file, int line) {
+  if (c && e != cudaErrorMemoryAllocation && e != cudaErrorInvalidValue) c->poisoned = true;
+  return fail(IBX_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+                                std::to_string(line) + ")");
+}
+
+bool get_array(ibx_ctx* c, ibx_array h, ibx_ctx::Arr& out) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->arrays.find(h);
+  if (it == c->arrays.end()) return false;
+  out = it->second;
+  return true;
+}
+
+float* ensure_scratch(ibx_ctx* c, int64_t nfloats) {
+  if (nfloats <= c->scratch_cap) return c->d_scratch;
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  c->d_scratch = nullptr;
+  c->scratch_cap = 0;
+  if (cudaMalloc((void**)&c->d_scratch, (size_t)nfloats * sizeof(float)) != cudaSuccess) return nullptr;
+  c->scratch_cap = nfloats;
+  return c->d_scratch;
+}
+
+static void free_tables(ibx_domain& D) {
+  auto fr = [](auto*& p) { if (p) { cudaFree(p); p = nullptr; } };
+  for (auto& P : D.parts) {
+    fr(P.d_domain); fr(P.d_image_in_domain); fr(P.d_spacing); fr(P.d_centers);
+    for (auto& T : P.dims) { fr(T.d_owners); fr(T.d_neighbors); fr(T.d_lptr); fr(T.d_lidx); fr(T.d_rptr); fr(T.d_ridx); }
+  }
+  for (auto& F : D.boundaries)
+    for (auto& B : F.parts) { fr(B.d_ghost); fr(B.d_ptr); fr(B.d_idx_global); fr(B.d_image_domain); fr(B.d_idx); fr(B.d_w); fr(B.d_normals); fr(B.d_eta); }
+  for (auto& S : D.surfaces) fr(S.d_areas);
+  fr(D.d_block_faces); fr(D.d_block_h);
+  for (auto& p : D.shard.d_send) fr(p);
+  for (auto& p : D.shard.d_recv) fr(p);
+  for (auto& p : D.shard.d_sendbuf) fr(p);
+  for (auto& p : D.shard.d_recvbuf) fr(p);
+  D.uploaded = false;
+}
+
+}  // namespace ibx
+
+ibx_domain::~ibx_domain() {
+  if (uploaded) { cudaSetDevice(device); ibx::free_tables(*this); }
+}
+
+ibx_accum::~ibx_accum() {
+  if (uploaded) { cudaFree(d_ptr); cudaFree(d_idx); if (d_w) cudaFree(d_w); }
+}
+
+using namespace ibx;
+
+extern "C" {
+
+int ibx_init(int device, ibx_ctx** out) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(IBX_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                  "); libibx has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(IBX_ERR_ARG, "ibx_init: device index out of range");
+  cudaDeviceProp prop;
+  ibx_ctx* c = new ibx_ctx();
+  c->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete c;
+    return fail(IBX_ERR_CUDA, std::string("ibx_init: ") + cudaGetErrorString(e));
+  }
+  if (prop.major < 10) {
+    delete c;
+    return fail(IBX_ERR_UNSUPPORTED, "ibx_init: libibx is built for sm_100a only; device is sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor));
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->total_mem = prop.totalGlobalMem;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&c->ev0));
+  CU(cudaEventCreate(&c->ev1));
+  CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  c->red_cap = 4096;
+  CU(cudaMalloc((void**)&c->d_red, c->red_cap * sizeof(double)));
+  CU(cudaMallocHost((void**)&c->h_red, c->red_cap * sizeof(double)));
+  *out = c;
+  return IBX_OK;
+}
+
+int ibx_finalize(ibx_ctx* c) {
+  if (!c) return IBX_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : c->arrays) cudaFree(kv.second.p);
+  if (c->d_red) cudaFree(c->d_red);
+  if (c->h_red) cudaFreeHost(c->h_red);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  delete c;
+  return IBX_OK;
+}
+
+int ibx_sync(ibx_ctx* c) {
+  CHECK_CTX(c);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->comm_stream));
+  return IBX_OK;
+}
+
+int ibx_device_info(ibx_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem) {
+  CHECK_CTX(c);
+  *sm_count = c->sm_count;
+  *cc_major = c->cc_major;
+  *cc_minor = c->cc_minor;
+  *total_mem = (int64_t)c->total_mem;
+  return IBX_OK;
+}
+
+int ibx_launch_count(ibx_ctx* c, int64_t* out) {
+  CHECK_CTX(c);
+  *out = c->launches;
+  return IBX_OK;
+}
+
+int ibx_timer_start(ibx_ctx* c) {
+  CHECK_CTX(c);
+  CU(cudaEventRecord(c->ev0, c->stream));
+  return IBX_OK;
+}
+
+int ibx_timer_stop(ibx_ctx* c, float* ms) {
+  CHECK_CTX(c);
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaEventSynchronize(c->ev1));
+  CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return IBX_OK;
+}
+
+int ibx_array_alloc(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out) {
+  CHECK_CTX(c);
+  if (rows < 0 || cols < 1) return fail(IBX_ERR_ARG, "ibx_array_alloc: rows >= 0 and cols >= 1 required");
+  float* p = nullptr;
+  size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * sizeof(float);
+  CU(cudaMalloc((void**)&p, bytes));
+  std::lock_guard<std::mutex> lk(c->mu);
+  int64_t h = c->next_handle++;
+  c->arrays[h] = {p, rows, cols};
+  *out = h;
+  return IBX_OK;
+}
+
+int ibx_array_free(ibx_ctx* c, ibx_array a) {
+  if (!c) return fail(IBX_ERR_ARG, "ibx_array_free: null context");
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->arrays.find(a);
+  if (it == c->arrays.end()) return fail(IBX_ERR_ARG, "ibx_array_free: invalid handle");
+  cudaStreamSynchronize(c->stream);
+  cudaFree(it->second.p);
+  c->arrays.erase(it);
+  return IBX_OK;
+}
+
+int ibx_array_shape(ibx_ctx* c, ibx_array a, int64_t* rows, int64_t* cols) {
+  CHECK_CTX(c);
+  GET_ARR(A, a);
+  *rows = A.rows;
+  *cols = A.cols;
+  return IBX_OK;
+}
+
+int ibx_array_upload(ibx_ctx* c, ibx_array a, const float* host) {
+  CHECK_CTX(c);
+  GET_ARR(A, a);
+  CU(cudaMemcpyAsync(A.p, host, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return IBX_OK;
+}
+
+int ibx_array_download(ibx_ctx* c, ibx_array a, float* host) {
+  CHECK_CTX(c);
+  GET_ARR(A, a);
+  CU(cudaMemcpyAsync(host, A.p, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return IBX_OK;
+}
+
+int ibx_array_copy(ibx_ctx* c, ibx_array dst, ibx_array src) {
+  CHECK_CTX(c);
+  GET_ARR(A, dst);
+  GET_ARR(B, src);
+  if (A.rows != B.rows || A.cols != B.cols) return fail(IBX_ERR_ARG, "ibx_array_copy: shape mismatch");
+  CU(cudaMemcpyAsync(A.p, B.p, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  return IBX_OK;
+}
+
+int ibx_array_devptr(ibx_ctx* c, ibx_array a, void** ptr) {
+  CHECK_CTX(c);
+  GET_ARR(A, a);
+  *ptr = A.p;
+  return IBX_OK;
+}
+
+int ibx_host_alloc(int64_t bytes, void** out) {
+  cudaError_t e = cudaMallocHost(out, (size_t)bytes);
+  if (e != cudaSuccess) return fail(IBX_ERR_CUDA, std::string("ibx_host_alloc: ") + cudaGetErrorString(e));
+  return IBX_OK;
+}
+
+int ibx_host_free(void* p) {
+  cudaFreeHost(p);
+  return IBX_OK;
+}
+
+int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
+  CHECK_CTX(c);
+  ibx_domain* Dp = find_domain(d);
+  if (!Dp) return fail(IBX_ERR_ARG, "ibx_domain_upload: unknown domain handle");
+  ibx_domain& D = *Dp;
+  if (D.uploaded) return IBX_OK;
+  int nd = D.nd;
+  D.device = c->device;
+  D.uploaded = true;  // so that a partial upload is released by the destructor
+  const int64_t* l2g = nullptr;
+  (void)l2g;
+  for (auto& P : D.parts) {
+    int rc;
+    if ((rc = upload_vec(c, P.domain, &P.d_domain))) return rc;
+    if ((rc = upload_vec(c, P.image_in_domain, &P.d_image_in_domain))) return rc;
+    int64_t n = (int64_t)P.domain.size();
+    std::vector<float> sp((size_t)n * nd), ce((size_t)n * nd);
+    for (int64_t i = 0; i < n; ++i)
+      for (int k = 0; k < nd; ++k) {
+        sp[(size_t)k * n + i] = D.widths[(size_t)P.domain[i] * nd + k];
+        ce[(size_t)k * n + i] = D.centers[(size_t)P.domain[i] * nd + k];
+      }
+    if ((rc = upload_vec(c, sp, &P.d_spacing))) return rc;
+    if ((rc = upload_vec(c, ce, &P.d_centers))) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& T : P.dims) {
+      if ((rc = upload_vec(c, T.owners, &T.d_owners))) return rc;
+      if ((rc = upload_vec(c, T.neighbors, &T.d_neighbors))) return rc;
+      if ((rc = upload_vec(c, T.lptr, &T.d_lptr))) return rc;
+      if ((rc = upload_vec(c, T.lidx, &T.d_lidx))) return rc;
+      if ((rc = upload_vec(c, T.rptr, &T.d_rptr))) return rc;
+      if ((rc = upload_vec(c, T.ridx, &T.d_ridx))) return rc;
+    }
+  }
+  for (auto& F : D.boundaries)
+    for (auto& B : F.parts) {
+      int rc;
+      int64_t G = (int64_t)B.ghost.size();
+      std::vector<int32_t> gidx(B.idx.size());
+      for (size_t q = 0; q < B.idx.size(); ++q) gidx[q] = B.image_domain[B.idx[q]];
+      std::vector<float> nrm((size_t)G * nd), eta(G);
+      for (int64_t g = 0; g < G; ++g) {
+        eta[g] = B.ghost_dist[g] / B.image_dist[g];  // eta, src/ImmersedBoundary.jl:1220
+        for (int k = 0; k < nd; ++k) nrm[(size_t)k * G + g] = B.normals[(size_t)g * nd + k];
+      }
+      if ((rc = upload_vec(c, B.ghost, &B.d_ghost))) return rc;
+      if ((rc = upload_vec(c, B.ptr, &B.d_ptr))) return rc;
+      if ((rc = upload_vec(c, gidx, &B.d_idx_global))) return rc;
+      if ((rc = upload_vec(c, B.image_domain, &B.d_image_domain))) return rc;
+      if ((rc = upload_vec(c, B.idx, &B.d_idx))) return rc;
+      if ((rc = upload_vec(c, B.w, &B.d_w))) return rc;
+      if ((rc = upload_vec(c, nrm, &B.d_normals))) return rc;
+      if ((rc = upload_vec(c, eta, &B.d_eta))) return rc;
+      CU(cudaStreamSynchronize(c->stream));
+    }
+  for (auto& S : D.surfaces) {
+    int rc;
+    if ((rc = upload_vec(c, S.areas, &S.d_areas))) return rc;
+    for (ibx_accum* A : {&S.interp, &S.offset_interp}) {
+      if ((rc = upload_vec(c, A->ptr, &A->d_ptr))) return rc;
+      if ((rc = upload_vec(c, A->idx, &A->d_idx))) return rc;
+      if ((rc = upload_vec(c, A->w, &A->d_w))) return rc;
+      A->uploaded = true;
+    }
+  }
+  {
+    int rc;
+    if ((rc = upload_vec(c, D.block_faces, &D.d_block_faces))) return rc;
+    if ((rc = upload_vec(c, D.block_h, &D.d_block_h))) return rc;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return IBX_OK;
+}
+
+int ibx_accum_upload(ibx_ctx* c, ibx_accum* a) {
+  CHECK_CTX(c);
+  ibx_accum* A = find_accum(a);
+  if (!A) return fail(IBX_ERR_ARG, "ibx_accum_upload: unknown accumulator handle");
+  if (A->uploaded) return IBX_OK;
+  int rc;
+  if ((rc = upload_vec(c, A->ptr, &A->d_ptr))) return rc;
+  if ((rc = upload_vec(c, A->idx, &A->d_idx))) return rc;
+  if (A->weighted && (rc = upload_vec(c, A->w, &A->d_w))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  A->uploaded = true;
+  return IBX_OK;
+}
+
+}  // extern "C"

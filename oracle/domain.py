@@ -278,7 +278,7 @@ class Domain:
         for bname, dfield in msh.distance_fields.items():
             g, p = ghosts_and_projections_surface(dfield, centers, widths, ghost_layer_ratio)
             self.boundaries[bname] = boundary_partitions(centers, widths, tree, g, p, max_partition_size, ghost_layer_ratio)
-            if not build_surfaces:
+            if not build_surfaces or dfield.stl is None:
                 continue
             stl = dfield.stl  # :743-763
             fcenters, fnormals = centers_and_normals(stl)

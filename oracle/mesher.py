@@ -63,7 +63,7 @@ class Line:
 
     def __call__(self, pt):
         v = pt - self.p1
-        xi = np.dot(self.m, v) / np.dot(self.m, self.m)
+        xi = np.dot(self.m / np.dot(self.m, self.m), v)  # `m \\ v` == pinv(m) * v
         if xi < 0.0:
             return norm(pt - self.p1)
         if xi > 1.0:
@@ -140,6 +140,8 @@ def write_stl_binary(fname, points, simplices):
 
 def merge_points(*stls, tolerance=1e-7, clean_degenerate=True):
     """``merge_points``, ``src/mesher.jl:351-407``."""
+    if not isinstance(tolerance, np.floating):
+        tolerance = np.float64(tolerance)  # a Julia Float64 literal promotes Float32 points (NumPy's would not)
     tag2ind = {}
     new_points = []
     new_simplices = []
@@ -410,8 +412,11 @@ def refine_orderly(surfaces, refinement_regions=(), ratio=F32(0.5), growth_ratio
     for i in order:
         stl, h = surfaces[i]
         h = h * ratio
-        stl = refine_to_length(stl, h, tolerance=tolerance, refinement_regions=regions, growth_ratio=growth_ratio)
-        dfield = DistanceField(stl)
+        if isinstance(stl, AnalyticSphere):
+            dfield = stl
+        else:
+            stl = refine_to_length(stl, h, tolerance=tolerance, refinement_regions=regions, growth_ratio=growth_ratio)
+            dfield = DistanceField(stl)
         result[int(i)] = dfield
         regions.append((dfield, h))
     return [result[i] for i in range(len(surfaces))]
@@ -433,9 +438,10 @@ class Mesh:
         dfields = refine_orderly([(stl, h) for _, stl, h in surfaces], refinement_regions=refinement_regions,
                                  growth_ratio=growth_ratio, tolerance=tolerance)
         self.distance_fields = {s[0]: df for s, df in zip(surfaces, dfields)}
-        regions = [(df, h * block_size) for df, h in refinement_regions]
+        tb = lambda h: h * type(h)(block_size) if isinstance(h, np.floating) else h * float(block_size)
+        regions = [(df, tb(h)) for df, h in refinement_regions]
         for name, _, h in surfaces:
-            regions.append((self.distance_fields[name], h * block_size))
+            regions.append((self.distance_fields[name], tb(h)))
         self.block_origins, self.block_widths = refine_octree(regions, self.origin, self.widths, growth_ratio)
 
     @classmethod
@@ -467,3 +473,26 @@ def get_cells(msh):
     centers = inner[None, :, :] * msh.block_widths[:, None, :] + msh.block_origins[:, None, :]
     widths = np.repeat((msh.block_widths / F32(bs))[:, None, :], bs ** nd, axis=1)
     return centers.reshape(-1, nd).astype(F32), widths.reshape(-1, nd).astype(F32)
+
+
+class AnalyticSphere:
+    """Oracle twin of the product's analytic sphere surface (extension, see include/ibx.h ``ibx_surface``):
+    exact unsigned distance / projection in float64 instead of an STL distance field."""
+
+    stl = None
+
+    def __init__(self, center, radius):
+        self.center = np.asarray(center, dtype=np.float64)
+        self.radius = float(radius)
+
+    def __call__(self, x):
+        return np.float64(abs(np.sqrt(np.sum((np.asarray(x, dtype=np.float64) - self.center) ** 2)) - self.radius))
+
+    def distances(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        return np.abs(np.sqrt(np.sum((X - self.center) ** 2, axis=1)) - self.radius)
+
+    def projection(self, X, R):
+        v = np.asarray(X, dtype=np.float64) - self.center
+        s = np.sqrt(np.sum(v ** 2, axis=1))
+        return self.center + v * (self.radius / s)[:, None]
