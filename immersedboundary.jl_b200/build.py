@@ -11,6 +11,8 @@ LIB = os.path.join(HERE, "libibx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOSTFLAGS = "-fPIC,-fopenmp,-ffp-contract=off,-Wall,-Wno-unused-variable,-Wno-unused-function"
+# ops.cu / cfd.cu reproduce the reference's separate float32 roundings bit for bit: no FMA contraction there
+NOFMA = ["-fmad=false"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", HOSTFLAGS]
 
 
@@ -32,7 +34,8 @@ def build(force=False, verbose=False):
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ, src + ".o")
         if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hm):
-            cmd = [NVCC] + ARCH + COMMON + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
+            extra = NOFMA if src in ("ops.cu", "cfd.cu") else []
+            cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
             if src.endswith(".cpp"):
                 cmd = [NVCC] + COMMON + ["-x", "cu"] * 0 + ["-c", sp, "-o", op]
             jobs.append((src, cmd))

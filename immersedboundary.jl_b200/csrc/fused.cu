@@ -1,0 +1,694 @@
+// Fused, block-structured residual kernels: the throughput path.
+//
+// Connectivity is implicit.  Inside a bs^nd block neighbours are index arithmetic; across a block face the
+// per-block BlockFace table (6 entries of 28 B per 512 cells = 0.33 B/cell) names the same-level, coarser
+// (2:1) or finer (1:2) neighbour block(s), or the domain box.  No per-cell/per-face index table is read,
+// which is what lets the path approach the algorithmic traffic of SURVEY.md section 8(d).
+//
+// Semantics are those of the reference operators evaluated on ONE partition covering the whole domain
+// (src/ImmersedBoundary.jl:605-698, :879-1157): a box face is a face whose owner and neighbour are the
+// same cell; a coarse cell's list towards finer cells holds 2^(nd-1) faces in ascending cell order,
+// averaged with weight 1/len.  Image-cell results do not depend on the partitioning because the skirt
+// is 2 deep, so this equals the reference's per-partition evaluation followed by its scatter.
+#include "device.cuh"
+
+using namespace ibx;
+
+namespace {
+
+constexpr int TB = 256;
+
+struct Topo {
+  const BlockFace* __restrict__ faces;
+  const float* __restrict__ h;  // nblocks x nd cell widths
+  int bs, log_cpb_unused;
+  int64_t cpb;
+  int64_t ncells;     // rows of every field array (owned + halo cells on a shard)
+  int64_t n_compute;  // cells whose residual is wanted (the owned range, stored first)
+};
+
+template <int ND>
+struct Nbr {
+  int cnt;
+  int64_t cell[ND == 3 ? 4 : 2];
+  float h;  // neighbour spacing along the face normal
+};
+
+template <int ND>
+__device__ __forceinline__ void decode(const Topo& T, int64_t cell, int64_t& b, int (&ii)[ND]) {
+  b = cell / T.cpb;
+  int l = (int)(cell - b * T.cpb);
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    ii[d] = l % T.bs;
+    l /= T.bs;
+  }
+}
+
+template <int ND>
+__device__ __forceinline__ int64_t encode(const Topo& T, int64_t b, const int (&ii)[ND]) {
+  int64_t l = 0;
+#pragma unroll
+  for (int d = ND - 1; d >= 0; --d) l = l * T.bs + ii[d];
+  return b * T.cpb + l;
+}
+
+// neighbours of `cell` across its (d, side) face; side 0 = low (left list), 1 = high (right list)
+template <int ND>
+__device__ __forceinline__ Nbr<ND> neighbors(const Topo& T, int64_t cell, int64_t b, const int (&ii)[ND], int d, int side) {
+  Nbr<ND> out;
+  const int bs = T.bs;
+  float hc = T.h[b * ND + d];
+  if ((side == 0 && ii[d] > 0) || (side == 1 && ii[d] < bs - 1)) {
+    int64_t stride = 1;
+    for (int k = 0; k < d; ++k) stride *= bs;
+    out.cnt = 1;
+    out.cell[0] = side ? cell + stride : cell - stride;
+    out.h = hc;
+    return out;
+  }
+  const BlockFace bf = T.faces[b * (2 * ND) + 2 * d + side];
+  int jj[ND];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) jj[k] = ii[k];
+  jj[d] = side ? 0 : bs - 1;
+  // tangential dims in increasing order
+  int t1 = d == 0 ? 1 : 0;
+  int t2 = ND == 3 ? (d == 2 ? 1 : 2) : t1;
+  switch (bf.kind) {
+    case 1:
+      out.cnt = 1;
+      out.cell[0] = encode<ND>(T, bf.nb[0], jj);
+      out.h = hc;
+      break;
+    case 2:
+      jj[t1] = (ii[t1] + bf.sub[0] * bs) >> 1;
+      if (ND == 3) jj[t2] = (ii[t2] + bf.sub[1] * bs) >> 1;
+      out.cnt = 1;
+      out.cell[0] = encode<ND>(T, bf.nb[0], jj);
+      out.h = hc * 2.0f;
+      break;
+    case 3: {
+      int half = bs >> 1;
+      int s1 = ii[t1] >= half, s2 = ND == 3 ? (ii[t2] >= half) : 0;
+      int64_t nb = bf.nb[s1 + 2 * s2];
+      int b1 = 2 * (ii[t1] - s1 * half), b2 = ND == 3 ? 2 * (ii[t2] - s2 * half) : 0;
+      out.cnt = ND == 3 ? 4 : 2;
+      out.h = hc * 0.5f;
+#pragma unroll
+      for (int q = 0; q < (ND == 3 ? 4 : 2); ++q) {
+        jj[t1] = b1 + (q & 1);
+        if (ND == 3) jj[t2] = b2 + (q >> 1);
+        out.cell[q] = encode<ND>(T, nb, jj);
+      }
+      break;
+    }
+    default:  // domain box: the face's owner and neighbour are both this cell
+      out.cnt = 1;
+      out.cell[0] = cell;
+      out.h = hc;
+      break;
+  }
+  return out;
+}
+
+__device__ __forceinline__ float clampT(float T) { return fmaxf(T, 10.0f); }
+__device__ __forceinline__ float sgn(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }
+__device__ __forceinline__ float face_interp(float uo, float un, float ho, float hn) { return (uo * hn + un * ho) / (hn + ho); }
+
+// ------------------------------------------------------------------ pass 1a: Q -> P
+template <int ND>
+__global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float rho = Q[i], E = Q[n + i];
+    float u[ND], k = 0.0f;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      u[d] = Q[(int64_t)(2 + d) * n + i] / rho;
+      k = d == 0 ? u[d] * u[d] : k + u[d] * u[d];
+    }
+    k = k / 2.0f;
+    float p = (f.gamma - 1.0f) * (E - rho * k);
+    P[i] = p;
+    P[n + i] = clampT(p / (rho * f.R));
+#pragma unroll
+    for (int d = 0; d < ND; ++d) P[(int64_t)(2 + d) * n + i] = u[d];
+  }
+}
+
+// ------------------------------------------------------------------ pass 1b: JST sensor of a scalar, max over dims
+template <int ND>
+__device__ __forceinline__ float sensor_cell(const Topo& T, const float* __restrict__ p, int64_t cell, int64_t b,
+                                             const int (&ii)[ND]) {
+  float pc = p[cell];
+  float nu = 1e-7f;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    float g[2], a[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      Nbr<ND> nb = neighbors<ND>(T, cell, b, ii, d, side);
+      float w = 1.0f / (float)nb.cnt;
+      float accg = 0.0f, acca = 0.0f;
+      for (int k = 0; k < nb.cnt; ++k) {
+        float pn = p[nb.cell[k]];
+        float fd = side ? pn - pc : pc - pn;  // p_neighbour - p_owner
+        accg = k == 0 ? fd * w : accg + fd * w;
+        acca = k == 0 ? fabsf(fd) * w : acca + fabsf(fd) * w;
+      }
+      g[side] = accg;
+      a[side] = acca;
+    }
+    float hc = T.h[b * ND + d];
+    float gg = (g[1] - g[0]) / hc, ugg = (a[1] + a[0]) / hc;
+    nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ugg));
+  }
+  return nu;
+}
+
+template <int ND>
+__global__ void k_sensor(Topo T, const float* __restrict__ p, float* __restrict__ D) {
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < T.ncells; cell += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b;
+    int ii[ND];
+    decode<ND>(T, cell, b, ii);
+    D[cell] = sensor_cell<ND>(T, p, cell, b, ii);
+  }
+}
+
+// ------------------------------------------------------------------ pass 2: gradients, MUSCL, flux, divergence
+// gradient along d of NV variables at an arbitrary cell (Green-Gauss over its two face lists)
+template <int ND, int NV>
+__device__ __forceinline__ void cell_grad(const Topo& T, const float* __restrict__ U, int64_t cell, int d, float* g) {
+  int64_t b;
+  int ii[ND];
+  decode<ND>(T, cell, b, ii);
+  float hc = T.h[b * ND + d];
+  float uc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) uc[v] = U[(int64_t)v * T.ncells + cell];
+  float m[2][NV];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    Nbr<ND> nb = neighbors<ND>(T, cell, b, ii, d, side);
+    float w = 1.0f / (float)nb.cnt;
+    for (int k = 0; k < nb.cnt; ++k) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float un = U[(int64_t)v * T.ncells + nb.cell[k]];
+        // at_faces: owner is the low-side cell; the formula is symmetric in (value, spacing) pairs
+        float fv = side ? face_interp(uc[v], un, hc, nb.h) : face_interp(un, uc[v], nb.h, hc);
+        m[side][v] = k == 0 ? fv * w : m[side][v] + fv * w;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v] = (m[1][v] - m[0][v]) / hc;
+}
+
+template <int NV>
+__device__ __forceinline__ void muscl_face(const float* uo, const float* un, const float* duo, const float* dun, float ho,
+                                           float hn, float Do, float Dn, bool use_D, bool high_order, float* uL, float* uR) {
+  float down = ho / 2.0f, dnei = hn / 2.0f;
+  float Df = fmaxf(fmaxf(Do, Dn), 1e-7f);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float gf = (un[v] - uo[v]) / (down + dnei);
+    float gu = (2.0f * duo[v] - gf) * down;
+    float Du = (2.0f * dun[v] - gf) * dnei;
+    float s = fminf(fabsf(Du), fabsf(gu)) * (sgn(Du) + sgn(gu)) / 2.0f;
+    float l = uo[v] + s, r = un[v] - s;
+    if (use_D) {
+      float uf = (uo[v] * dnei + un[v] * down) / (down + dnei);
+      if (high_order) uf = uf + (duo[v] * down - dun[v] * dnei) / 8.0f;
+      l = l * Df + (1.0f - Df) * uf;
+      r = r * Df + (1.0f - Df) * uf;
+    }
+    uL[v] = l;
+    uR[v] = r;
+  }
+}
+
+template <int ND>
+__device__ __forceinline__ void p2s(ibx_fluid f, const float* P, float* Q) {
+  float T = clampT(P[1]);
+  float k = P[2] * P[2];
+#pragma unroll
+  for (int d = 1; d < ND; ++d) k = k + P[2 + d] * P[2 + d];
+  k = k / 2.0f;
+  float rho = P[0] / (f.R * T);
+  Q[0] = rho;
+  Q[1] = rho * (f.R / (f.gamma - 1.0f) * T + k);
+#pragma unroll
+  for (int d = 0; d < ND; ++d) Q[2 + d] = rho * P[2 + d];
+}
+
+template <int ND>
+__device__ __forceinline__ void s2p(ibx_fluid f, const float* Q, float* P) {
+  float rho = Q[0];
+  float k = 0.0f;
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    P[2 + d] = Q[2 + d] / rho;
+    k = d == 0 ? P[2] * P[2] : k + P[2 + d] * P[2 + d];
+  }
+  k = k / 2.0f;
+  float p = (f.gamma - 1.0f) * (Q[1] - rho * k);
+  P[0] = p;
+  P[1] = clampT(p / (rho * f.R));
+}
+
+// HLL flux of src/cfd.jl:459-508 (float32 throughout; the reference's accidental Float64 promotion of the
+// last line is within the 1e-5 parity tolerance)
+template <int ND>
+__device__ __forceinline__ void hll_flux(ibx_fluid f, const float* pl, const float* pr, int dim, float* F) {
+  constexpr int NV = ND + 2;
+  float ql[NV], qr[NV];
+  p2s<ND>(f, pl, ql);
+  p2s<ND>(f, pr, qr);
+  float gr = f.gamma * f.R;
+  float uL = pl[2 + dim], uR = pr[2 + dim];
+  float aL = sqrtf(gr * clampT(pl[1])), aR = sqrtf(gr * clampT(pr[1]));
+  float SR = fminf(uR - aR, 0.0f), SL = fmaxf(uL + aL, 0.0f);
+  float inv = 1.0f / (SL - SR);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float l = ql[v], r = qr[v];
+    if (v == 1) { l += pl[0]; r += pr[0]; }
+    l *= uL;
+    r *= uR;
+    if (v == 2 + dim) { l += pl[0]; r += pr[0]; }
+    F[v] = (SL * l - SR * r + SR * SL * (qr[v] - ql[v])) * inv;
+  }
+}
+
+// sensor-Rusanov flux of src/cfd.jl:516-554 with nuL = nuR = nu
+template <int ND>
+__device__ __forceinline__ void rusanov_flux(ibx_fluid f, const float* pl, const float* pr, float nu, int dim, float* F) {
+  constexpr int NV = ND + 2;
+  float ul[NV], ur[NV], pm[NV];
+  p2s<ND>(f, pl, ul);
+  p2s<ND>(f, pr, ur);
+  ul[1] += pl[0];
+  ur[1] += pr[0];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) pm[v] = (pl[v] + pr[v]) / 2.0f;
+  float u = pm[2 + dim];
+  float a = sqrtf(f.gamma * f.R * clampT(pm[1]));
+  float diss = nu * (a + fabsf(u)) / 2.0f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float fv = (ul[v] + ur[v]) * u / 2.0f;
+    if (v == 2 + dim) fv += pm[0];
+    F[v] = fv + (ul[v] - ur[v]) * diss;
+  }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(TB) k_euler_flux(Topo T, ibx_fluid f, int flux_kind, const float* __restrict__ P,
+                                                   const float* __restrict__ D, float* __restrict__ R, float* __restrict__ cfl) {
+  constexpr int NV = ND + 2;
+  const int64_t N = T.ncells;
+  const float gr = f.gamma * f.R;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < T.n_compute; cell += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b;
+    int ii[ND];
+    decode<ND>(T, cell, b, ii);
+    float pc[NV], res[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { pc[v] = P[(int64_t)v * N + cell]; res[v] = 0.0f; }
+    float Dc = D[cell];
+    float ac = sqrtf(gr * clampT(pc[1]));
+    float cf = 0.0f;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float hc = T.h[b * ND + d];
+      float gc[NV];
+      cell_grad<ND, NV>(T, P, cell, d, gc);
+      float msum[2][NV], csum[2];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        Nbr<ND> nb = neighbors<ND>(T, cell, b, ii, d, side);
+        float w = 1.0f / (float)nb.cnt;
+        for (int k = 0; k < nb.cnt; ++k) {
+          int64_t n = nb.cell[k];
+          float pn[NV], gn[NV], F[NV], pl[NV], pr[NV];
+          float Dn;
+          if (n == cell) {  // box face
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { pn[v] = pc[v]; gn[v] = gc[v]; }
+            Dn = Dc;
+          } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) pn[v] = P[(int64_t)v * N + n];
+            cell_grad<ND, NV>(T, P, n, d, gn);
+            Dn = D[n];
+          }
+          float an = sqrtf(gr * clampT(pn[1]));
+          float uf, af;
+          if (side) {  // this cell is the owner
+            muscl_face<NV>(pc, pn, gc, gn, hc, nb.h, Dc, Dn, true, false, pl, pr);
+            uf = face_interp(pc[2 + d], pn[2 + d], hc, nb.h);
+            af = face_interp(ac, an, hc, nb.h);
+          } else {     // the neighbour entry is the owner
+            muscl_face<NV>(pn, pc, gn, gc, nb.h, hc, Dn, Dc, true, false, pl, pr);
+            uf = face_interp(pn[2 + d], pc[2 + d], nb.h, hc);
+            af = face_interp(an, ac, nb.h, hc);
+          }
+          if (flux_kind == 0) {
+            hll_flux<ND>(f, pl, pr, d, F);
+          } else {
+            float nu = side ? face_interp(Dc, Dn, hc, nb.h) : face_interp(Dn, Dc, nb.h, hc);
+            rusanov_flux<ND>(f, pl, pr, nu, d, F);
+          }
+          float ct = (fabsf(uf) + af) * w;
+          csum[side] = k == 0 ? ct : csum[side] + ct;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) msum[side][v] = k == 0 ? F[v] * w : msum[side][v] + F[v] * w;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) res[v] = res[v] - (msum[1][v] - msum[0][v]) / hc;
+      cf = cf + (csum[1] + csum[0]) / hc;
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) R[(int64_t)v * N + cell] = res[v];
+    cfl[cell] = cf;
+  }
+}
+
+// linear advection of test/advection.jl:67-83: ud = -sum_d GG((uL+uR) Cf / 2 + |Cf| (uL-uR) / 2),
+// spec = max_d UGG(at_faces(C_d))
+template <int ND>
+__global__ void __launch_bounds__(TB) k_advection(Topo T, const float* __restrict__ u, const float* __restrict__ C,
+                                                  const float* __restrict__ D, float* __restrict__ ud, float* __restrict__ spec) {
+  const int64_t N = T.ncells;
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < T.n_compute; cell += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b;
+    int ii[ND];
+    decode<ND>(T, cell, b, ii);
+    float uc = u[cell], Dc = D[cell];
+    float res = 0.0f, sp = 0.0f;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float hc = T.h[b * ND + d];
+      float cc = C[(int64_t)d * N + cell];
+      float gc;
+      cell_grad<ND, 1>(T, u, cell, d, &gc);
+      float msum[2], csum[2];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        Nbr<ND> nb = neighbors<ND>(T, cell, b, ii, d, side);
+        float w = 1.0f / (float)nb.cnt;
+        for (int k = 0; k < nb.cnt; ++k) {
+          int64_t n = nb.cell[k];
+          float un = uc, gn = gc, Dn = Dc, cn = cc;
+          if (n != cell) {
+            un = u[n];
+            cell_grad<ND, 1>(T, u, n, d, &gn);
+            Dn = D[n];
+            cn = C[(int64_t)d * N + n];
+          }
+          float uL, uR, Cf;
+          if (side) {
+            muscl_face<1>(&uc, &un, &gc, &gn, hc, nb.h, Dc, Dn, true, true, &uL, &uR);
+            Cf = face_interp(cc, cn, hc, nb.h);
+          } else {
+            muscl_face<1>(&un, &uc, &gn, &gc, nb.h, hc, Dn, Dc, true, true, &uL, &uR);
+            Cf = face_interp(cn, cc, nb.h, hc);
+          }
+          float F = (uL + uR) * Cf / 2.0f + fabsf(Cf) * (uL - uR) / 2.0f;
+          msum[side] = k == 0 ? F * w : msum[side] + F * w;
+          csum[side] = k == 0 ? Cf * w : csum[side] + Cf * w;
+        }
+      }
+      res = res - (msum[1] - msum[0]) / hc;
+      float s = (csum[1] + csum[0]) / hc;
+      sp = d == 0 ? s : fmaxf(sp, s);
+    }
+    ud[cell] = res;
+    spec[cell] = sp;
+  }
+}
+
+// ------------------------------------------------------------------ IB ghost update on the conservative state
+struct BCParams {
+  float p_inf, T_inf, u_inf[3];
+  int normal_flow;
+};
+
+template <int ND>
+__global__ void k_ghost_stage(ibx_fluid f, BCParams bc, const float* __restrict__ Q, int64_t N,
+                              const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ w,
+                              const float* __restrict__ nrm, const float* __restrict__ eta, float* __restrict__ stage, int64_t G) {
+  constexpr int NV = ND + 2;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x) {
+    float ia[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ia[v] = 0.0f;
+    int32_t b0 = ptr[g], e0 = ptr[g + 1];
+    for (int32_t k = b0; k < e0; ++k) {
+      int64_t c = idx[k];
+      float q[NV], p[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) q[v] = Q[(int64_t)v * N + c];
+      s2p<ND>(f, q, p);
+      float wk = w[k];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) ia[v] = k == b0 ? p[v] * wk : ia[v] + p[v] * wk;
+    }
+    float n_[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) n_[d] = nrm[(int64_t)d * G + g];
+    // FlowBC (src/cfd.jl:243-300)
+    float un;
+    if (bc.normal_flow) {
+      un = bc.u_inf[0];
+    } else {
+      un = n_[0] * bc.u_inf[0];
+#pragma unroll
+      for (int d = 1; d < ND; ++d) un = un + n_[d] * bc.u_inf[d];
+    }
+    float cur = ia[2] * n_[0];
+#pragma unroll
+    for (int d = 1; d < ND; ++d) cur = cur + ia[2 + d] * n_[d];
+    float a = sqrtf(f.gamma * f.R * clampT(ia[1]));
+    float M = fabsf(un) / a;
+    float ba[NV];
+    bool sup = M > 1.0f;
+    ba[0] = un >= 0.0f ? (sup ? bc.p_inf : ia[0]) : (sup ? ia[0] : bc.p_inf);
+    ba[1] = un > 0.0f ? bc.T_inf : ia[1];
+    if (bc.normal_flow) {
+      float corr = un - cur;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) ba[2 + d] = ia[2 + d] + n_[d] * corr;
+    } else {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) ba[2 + d] = un < 0.0f ? ia[2 + d] : bc.u_inf[d];
+    }
+    float e = eta[g];
+    float pg[NV], qg[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) pg[v] = e * ia[v] + (1.0f - e) * ba[v];
+    p2s<ND>(f, pg, qg);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) stage[(int64_t)v * G + g] = qg[v];
+  }
+}
+
+__global__ void k_ghost_commit(const float* __restrict__ stage, const int32_t* __restrict__ ghost, float* __restrict__ Q,
+                               int64_t N, int64_t G, int nv) {
+  int64_t tot = G * nv;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = t % G, v = t / G;
+    Q[v * N + ghost[g]] = stage[t];
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ host entry points
+#define SHAPE(cond, msg) \
+  if (!(cond)) return fail(IBX_ERR_ARG, std::string(__func__) + ": shape mismatch: " + (msg))
+
+static int fused_grid(ibx_ctx* c, int64_t n) {
+  // whole waves of resident CTAs: multiples of the SM count (148 on B200)
+  int64_t g = (n + TB - 1) / TB;
+  int64_t wave = (int64_t)c->sm_count * 8;
+  if (g > wave) g = ((g + wave - 1) / wave > 4 ? 4 : (g + wave - 1) / wave) * wave;
+  return (int)std::max<int64_t>(g, 1);
+}
+
+static int check_fused(const ibx_domain& D, const char* fn) {
+  if (!D.two_to_one)
+    return fail(IBX_ERR_UNSUPPORTED, std::string(fn) + ": mesh has block contacts that are neither same-level nor 2:1; "
+                                                        "use the per-operator path");
+  if (D.block_size < 2 || (D.block_size & 1))
+    return fail(IBX_ERR_UNSUPPORTED, std::string(fn) + ": fused kernels need an even block_size >= 2");
+  return IBX_OK;
+}
+
+static Topo make_topo(const ibx_domain& D) {
+  Topo T;
+  T.faces = D.d_block_faces;
+  T.h = D.d_block_h;
+  T.bs = D.block_size;
+  T.log_cpb_unused = 0;
+  T.cpb = 1;
+  for (int d = 0; d < D.nd; ++d) T.cpb *= D.block_size;
+  T.ncells = D.ncells;
+  T.n_compute = D.shard.active ? D.shard.n_owned : D.ncells;
+  return T;
+}
+
+extern "C" {
+
+int ibx_residual_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, ibx_array Qh, ibx_array Rh, ibx_array cflh) {
+  CHECK_CTX(c);
+  GET_DOM(D, d);
+  int rc = check_fused(D, __func__);
+  if (rc) return rc;
+  GET_ARR(Q, Qh);
+  GET_ARR(R, Rh);
+  GET_ARR(CF, cflh);
+  int nv = D.nd + 2;
+  SHAPE(Q.rows == D.ncells && Q.cols == nv && R.rows == D.ncells && R.cols == nv && CF.rows == D.ncells && CF.cols == 1,
+        "Q, R must be ncells x (nd + 2); cfl ncells x 1");
+  if (flux_kind != 0 && flux_kind != 1) return fail(IBX_ERR_ARG, "ibx_residual_euler: flux_kind must be 0 (HLL) or 1 (sensor-Rusanov)");
+  int64_t N = D.ncells;
+  float* scratch = ensure_scratch(c, N * (nv + 1));
+  if (!scratch) return fail(IBX_ERR_CUDA, "ibx_residual_euler: out of device memory for the primitive/sensor scratch");
+  float* P = scratch;
+  float* S = scratch + N * nv;
+  Topo T = make_topo(D);
+  int g = fused_grid(c, N);
+  if (D.nd == 2) {
+    k_prim<2><<<g, TB, 0, c->stream>>>(f, Q.p, P, N);
+    LAUNCH_CHECK();
+    k_sensor<2><<<g, TB, 0, c->stream>>>(T, P, S);
+    LAUNCH_CHECK();
+    k_euler_flux<2><<<g, TB, 0, c->stream>>>(T, f, flux_kind, P, S, R.p, CF.p);
+    LAUNCH_CHECK();
+  } else {
+    k_prim<3><<<g, TB, 0, c->stream>>>(f, Q.p, P, N);
+    LAUNCH_CHECK();
+    k_sensor<3><<<g, TB, 0, c->stream>>>(T, P, S);
+    LAUNCH_CHECK();
+    k_euler_flux<3><<<g, TB, 0, c->stream>>>(T, f, flux_kind, P, S, R.p, CF.p);
+    LAUNCH_CHECK();
+  }
+  return IBX_OK;
+}
+
+int ibx_residual_advection(ibx_ctx* c, const ibx_domain* d, ibx_array uh, ibx_array Ch, ibx_array udh, ibx_array spech) {
+  CHECK_CTX(c);
+  GET_DOM(D, d);
+  int rc = check_fused(D, __func__);
+  if (rc) return rc;
+  GET_ARR(U, uh);
+  GET_ARR(C, Ch);
+  GET_ARR(UD, udh);
+  GET_ARR(SP, spech);
+  int64_t N = D.ncells;
+  SHAPE(U.rows == N && U.cols == 1 && C.rows == N && C.cols == D.nd && UD.rows == N && UD.cols == 1 && SP.rows == N && SP.cols == 1,
+        "u, ud, spec ncells x 1; C ncells x nd");
+  float* S = ensure_scratch(c, N);
+  if (!S) return fail(IBX_ERR_CUDA, "ibx_residual_advection: out of device memory");
+  Topo T = make_topo(D);
+  int g = fused_grid(c, N);
+  if (D.nd == 2) {
+    k_sensor<2><<<g, TB, 0, c->stream>>>(T, U.p, S);
+    LAUNCH_CHECK();
+    k_advection<2><<<g, TB, 0, c->stream>>>(T, U.p, C.p, S, UD.p, SP.p);
+    LAUNCH_CHECK();
+  } else {
+    k_sensor<3><<<g, TB, 0, c->stream>>>(T, U.p, S);
+    LAUNCH_CHECK();
+    k_advection<3><<<g, TB, 0, c->stream>>>(T, U.p, C.p, S, UD.p, SP.p);
+    LAUNCH_CHECK();
+  }
+  return IBX_OK;
+}
+
+int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow,
+                           ibx_array Qh) {
+  CHECK_CTX(c);
+  GET_DOM(D, d);
+  if (b < 0 || b >= (int)D.boundaries.size()) return fail(IBX_ERR_ARG, "ibx_ghost_update_euler: boundary index out of range");
+  GET_ARR(Q, Qh);
+  int nv = D.nd + 2;
+  SHAPE(Q.rows == D.ncells && Q.cols == nv, "Q must be ncells x (nd + 2)");
+  if (normal_flow) {
+    if (n_pinf != 3) return fail(IBX_ERR_ARG, "Only 3 parcels in P (p, T and normal flow) allowed for normal_flow = true BC");
+  } else if (n_pinf != nv) {
+    return fail(IBX_ERR_ARG, "ibx_ghost_update_euler: Pinf must hold p, T and nd velocity components");
+  }
+  BCParams bc{};
+  bc.p_inf = Pinf[0];
+  bc.T_inf = Pinf[1];
+  for (int k = 0; k < n_pinf - 2; ++k) bc.u_inf[k] = Pinf[2 + k];
+  bc.normal_flow = normal_flow;
+  int64_t Gtot = 0;
+  for (auto& B : D.boundaries[b].parts) Gtot += (int64_t)B.ghost.size();
+  if (Gtot == 0) return IBX_OK;
+  // the staging area lives after the residual scratch so both can coexist
+  int64_t N = D.ncells;
+  float* scratch = ensure_scratch(c, N * (nv + 1) + Gtot * nv);
+  if (!scratch) return fail(IBX_ERR_CUDA, "ibx_ghost_update_euler: out of device memory");
+  float* stage = scratch + N * (nv + 1);
+  int64_t off = 0;
+  // Jacobi across the chunks of one boundary: stage all, then commit all
+  for (auto& B : D.boundaries[b].parts) {
+    int64_t G = (int64_t)B.ghost.size();
+    int g = grid_for(G, 128, c->sm_count, 16);
+    if (D.nd == 2) k_ghost_stage<2><<<g, 128, 0, c->stream>>>(f, bc, Q.p, N, B.d_ptr, B.d_idx_global, B.d_w, B.d_normals, B.d_eta, stage + off * nv, G);
+    else k_ghost_stage<3><<<g, 128, 0, c->stream>>>(f, bc, Q.p, N, B.d_ptr, B.d_idx_global, B.d_w, B.d_normals, B.d_eta, stage + off * nv, G);
+    LAUNCH_CHECK();
+    off += G;
+  }
+  off = 0;
+  for (auto& B : D.boundaries[b].parts) {
+    int64_t G = (int64_t)B.ghost.size();
+    k_ghost_commit<<<grid_for(G * nv, TB, c->sm_count, 16), TB, 0, c->stream>>>(stage + off * nv, B.d_ghost, Q.p, N, G, nv);
+    LAUNCH_CHECK();
+    off += G;
+  }
+  return IBX_OK;
+}
+
+int ibx_euler_step_host(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                        const float* Q_host, float* R_host, float* cfl_host) {
+  CHECK_CTX(c);
+  GET_DOM(D, d);
+  int nv = D.nd + 2;
+  int64_t N = D.ncells;
+  int rc;
+  if (c->e2e_Q) {
+    ibx_ctx::Arr probe;
+    if (get_array(c, c->e2e_Q, probe) && (probe.rows != N || probe.cols != nv)) {
+      ibx_array_free(c, c->e2e_Q);
+      ibx_array_free(c, c->e2e_R);
+      ibx_array_free(c, c->e2e_cfl);
+      c->e2e_Q = 0;
+    }
+  }
+  if (!c->e2e_Q) {
+    if ((rc = ibx_array_alloc(c, N, nv, &c->e2e_Q))) return rc;
+    if ((rc = ibx_array_alloc(c, N, nv, &c->e2e_R))) return rc;
+    if ((rc = ibx_array_alloc(c, N, 1, &c->e2e_cfl))) return rc;
+  }
+  GET_ARR(Q, c->e2e_Q);
+  GET_ARR(R, c->e2e_R);
+  GET_ARR(CF, c->e2e_cfl);
+  if (Q.rows != N || Q.cols != nv) return fail(IBX_ERR_STATE, "ibx_euler_step_host: staging arrays belong to a different domain");
+  CU(cudaMemcpyAsync(Q.p, Q_host, (size_t)N * nv * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  for (int k = 0; k < nbc; ++k)
+    if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, c->e2e_Q))) return rc;
+  if ((rc = ibx_residual_euler(c, d, f, flux_kind, c->e2e_Q, c->e2e_R, c->e2e_cfl))) return rc;
+  CU(cudaMemcpyAsync(R_host, R.p, (size_t)N * nv * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(cfl_host, CF.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return IBX_OK;
+}
+
+}  // extern "C"

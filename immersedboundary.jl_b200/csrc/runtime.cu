@@ -156,6 +156,7 @@ int ibx_array_alloc(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out) {
   float* p = nullptr;
   size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * sizeof(float);
   CU(cudaMalloc((void**)&p, bytes));
+  CU(cudaMemsetAsync(p, 0, bytes, c->stream));
   std::lock_guard<std::mutex> lk(c->mu);
   int64_t h = c->next_handle++;
   c->arrays[h] = {p, rows, cols};
@@ -289,6 +290,13 @@ int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
       if ((rc = upload_vec(c, A->idx, &A->d_idx))) return rc;
       if ((rc = upload_vec(c, A->w, &A->d_w))) return rc;
       A->uploaded = true;
+    }
+  }
+  if (D.shard.active) {
+    int rc;
+    for (int peer = 0; peer < D.shard.nranks; ++peer) {
+      if ((rc = upload_vec(c, D.shard.send_local[peer], &D.shard.d_send[peer]))) return rc;
+      if ((rc = upload_vec(c, D.shard.recv_local[peer], &D.shard.d_recv[peer]))) return rc;
     }
   }
   {

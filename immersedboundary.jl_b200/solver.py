@@ -1,0 +1,152 @@
+"""Host-side mirrors of ``src/solver.jl`` (``FAS!``), ``src/mgrid.jl`` (``Multigrid``) and
+``src/point_implicit.jl`` (``linearize``/``solve``) driving device arrays: host recursion and scalars,
+all array work in libibx kernels."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import call, ptr
+from .domain import Accumulator, DeviceArray, context, dot
+
+F32 = np.float32
+EPS32 = np.finfo(np.float32).eps
+
+
+def FAS(f, Q, coarseners=(), prolongators=(), prescribed_f=None, multigrid_level=0, n_iter=50, rtol=1e-1, atol=1e-7):
+    """``FAS!`` (``src/solver.jl:39-91``) on ``DeviceArray``s; ``f(level, Q) -> (r, omega)``; mutates ``Q``.
+
+    Keeps the reference's ``length(coarseners) > 1`` quirk (``:60``)."""
+    l = multigrid_level
+    fQ, omega = f(l, Q)
+    source = None
+    if prescribed_f is not None:
+        source = prescribed_f - fQ
+    r = fQ if source is None else fQ + source
+    nr0 = float(r.norm())
+    nr = nr0
+    if len(coarseners) > 1:
+        Qc = coarseners[0](Q)
+        Qcold = Qc.copy()
+        pfQc = coarseners[0](r)
+        FAS(f, Qc, coarseners[1:], prolongators[1:], pfQc, l + 1, n_iter, rtol, atol)
+        Q += prolongators[0](Qc - Qcold)
+    for _ in range(n_iter):
+        r, omega = f(l, Q)
+        if source is not None:
+            r += source
+        om = omega if isinstance(omega, DeviceArray) else DeviceArray(Q.rows, 1, True).fill(omega)
+        call("ibx_clamped_update", context(), Q.h, om.h, r.h)
+        nr = float(r.norm())
+        if nr < nr0 * rtol + atol:
+            break
+    return nr / (nr0 + EPS32)
+
+
+class Multigrid:
+    """``GeometricMultigrid.Multigrid(X, n_levels, volumes)`` (``src/mgrid.jl:104-144``)."""
+
+    def __init__(self, X, n_levels, volumes=None):
+        X = np.ascontiguousarray(X, dtype=F32)
+        v = None if volumes is None else np.ascontiguousarray(volumes, dtype=F32)
+        self.coarseners, self.prolongators = [], []
+        for n in range(1, n_levels + 1):
+            c, p = C.c_void_p(), C.c_void_p()
+            call("ibx_mgrid_build", X.shape[1], X.shape[0], ptr(X), n, ptr(v), C.byref(c), C.byref(p))
+            self.coarseners.append(Accumulator(_handle=c))
+            self.prolongators.append(Accumulator(_handle=p))
+
+
+class PIPreconditioner:
+    """``PIPreconditioner`` (``src/point_implicit.jl:121-161``): per-cell block (or scalar) inverse."""
+
+    def __init__(self, D, nv=None):
+        self.nv = nv
+        if nv is None:  # scalar diagonal: 1 / (eps + D)
+            self.inv = (D + float(EPS32))._un(4)
+        else:
+            self.inv = DeviceArray(D.rows, nv * nv, False)
+            call("ibx_block_pinv", context(), D.h, nv, self.inv.h)
+
+    def __call__(self, v):
+        if self.nv is None:
+            return v * self.inv
+        out = DeviceArray(v.rows, v.cols, v.vector)
+        call("ibx_block_apply", context(), self.inv.h, self.nv, v.h, out.h)
+        return out
+
+
+def hutchinson_trick(f, X, n_samples, h=1e-6, fX=None, rng=None):
+    """``hutchinson_trick`` (``src/point_implicit.jl:18-91``) -> D (N x nv*nv, block (p, j, i) at column j + nv*i).
+
+    Every probe is one full evaluation of ``f``; +-1 probes come from a counter-free NumPy generator seeded by
+    the caller (the reference uses the global RNG)."""
+    rng = rng or np.random.default_rng(0)
+    fX = f(X) if fX is None else fX
+    N, nv = X.rows, X.cols
+    D = DeviceArray(N, nv * nv, False).fill(0.0)
+    for i in range(nv):
+        acc = DeviceArray(N, nv, False).fill(0.0)
+        for _ in range(n_samples):
+            z = rng.choice(np.array([-1.0, 1.0], dtype=F32), size=N)
+            dz = DeviceArray.from_host(z)
+            Xb = X.copy()
+            col = X.col(i) + dz * float(h)
+            call("ibx_array_set_column", context(), Xb.h, i, col.h)
+            J = (f(Xb) - fX) / float(h)
+            acc += J * dz
+        acc = acc / float(n_samples)
+        for j in range(nv):
+            call("ibx_array_set_column", context(), D.h, j + nv * i, acc.col(j).h)
+    return D
+
+
+class Linearization:
+    """``Linearization`` (``src/point_implicit.jl:98-114``): finite-difference Jacobian-vector product."""
+
+    def __init__(self, f, x, fx, h):
+        self.f, self.x, self.fx, self.h = f, x, fx, float(h)
+
+    def __call__(self, v):
+        return (self.f(self.x + v * self.h) - self.fx) / self.h
+
+
+def linearize(f, x, n_hutchinson_samples=30, pre_evaluated_fx=None, h=1e-6, rng=None):
+    """``linearize`` (``src/point_implicit.jl:184-207``) -> (A, b, D)."""
+    fx = f(x) if pre_evaluated_fx is None else pre_evaluated_fx.copy()
+    x = x.copy()
+    D = hutchinson_trick(f, x, n_hutchinson_samples, h, fx, rng)
+    return Linearization(f, x, fx, h), -fx, PIPreconditioner(D, x.cols)
+
+
+def proj_along(A, v, b):
+    """``proj_along`` (``src/point_implicit.jl:220-233``)."""
+    Av = A(v)
+    return dot(Av, b) / (dot(Av, Av) + float(EPS32)), Av
+
+
+def solve(A, b, prec, n_iter=100, n_inner=1, rtol=1e-2, atol=1e-7, multigrid=None):
+    """``solve`` (``src/point_implicit.jl:250-329``) -> (x, |r|/|r0|)."""
+    eps = float(EPS32)
+    nr0 = float(b.norm())
+    nr = nr0
+    x = b.like().fill(0.0)
+    r = b.copy()
+    n_levels = 0 if multigrid is None else len(multigrid.coarseners)
+    n_mgrid = n_levels
+    for _ in range(n_iter):
+        for _ in range(n_inner):
+            s = prec(r)
+            if n_mgrid > 0:
+                s = multigrid.prolongators[n_mgrid - 1](multigrid.coarseners[n_mgrid - 1](s))
+            alpha, As = proj_along(A, s, r)
+            x += s * alpha
+            r -= As * alpha
+            s = r / (eps + float(r.maxabs()))
+            alpha, As = proj_along(A, s, r)
+            x += s * alpha
+            r -= As * alpha
+            nr = float(r.norm())
+            if nr < nr0 * rtol + atol:
+                return x, nr / (nr0 + eps)
+        n_mgrid = n_levels if n_mgrid == 0 else n_mgrid - 1
+    return x, nr / (nr0 + eps)

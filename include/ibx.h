@@ -186,6 +186,8 @@ int ibx_array_download(ibx_ctx* c, ibx_array a, float* host);
 int ibx_array_fill(ibx_ctx* c, ibx_array a, float v);
 int ibx_array_copy(ibx_ctx* c, ibx_array dst, ibx_array src);
 int ibx_array_devptr(ibx_ctx* c, ibx_array a, void** ptr);
+int ibx_array_column(ibx_ctx* c, ibx_array a, int col, ibx_array out);        /* out (rows x 1) = a[:, col]  */
+int ibx_array_set_column(ibx_ctx* c, ibx_array a, int col, ibx_array src);    /* a[:, col] = src (rows x 1)  */
 /* pinned host staging buffers for the end-to-end path */
 int ibx_host_alloc(int64_t bytes, void** out);
 int ibx_host_free(void* p);
@@ -295,6 +297,9 @@ int ibx_shard_info(const ibx_domain* local, int64_t* n_owned, int64_t* n_halo, i
 int ibx_shard_tables(const ibx_domain* local, int32_t* local_to_global /* n_owned + n_halo */);
 int ibx_halo_sizes(const ibx_domain* local, int nranks, int64_t* send_counts, int64_t* recv_counts);
 int ibx_halo_lists(const ibx_domain* local, int peer, int32_t* send_local, int32_t* recv_local);
+/* tell this rank which of its cells `peer` needs (GLOBAL ids, in the peer's unpack order = recv_local order);
+ * the host program moves these lists between ranks (torch.distributed / MPI / files) before ibx_domain_upload */
+int ibx_shard_set_send(ibx_domain* local, int peer, int64_t n, const int32_t* global_ids);
 /* exchange the halo rows of `a` (n_owned + n_halo rows): pack -> ncclSend/Recv -> unpack, on the comm stream */
 int ibx_halo_begin(ibx_ctx* c, const ibx_domain* local, ibx_array a);
 int ibx_halo_end(ibx_ctx* c, const ibx_domain* local, ibx_array a);

@@ -75,17 +75,16 @@ def euler_residual(fluid, flux="hll"):
 def euler_ghost_update(dom, fluid, Q, bcs):
     """IB ghost update on the conservative state.
 
-    ``bcs`` is an ordered list of (boundary name, FlowBC).  Equivalent to
-    ``P = state2primitive(Q); impose_bc!(dom, name, P) do b, Pi; bc(Pi, b.normals) end`` for
-    every entry in order (each boundary Jacobi-style: all image reads before any ghost
-    write), then ``Q[ghosts] = primitive2state(P[ghosts])``.
+    ``bcs`` is an ordered list of (boundary name, FlowBC).  For every entry, in order:
+    ``P = state2primitive(Q); impose_bc!(dom, name, P) do b, Pi; bc(Pi, b.normals) end;
+    Q[ghosts] = primitive2state(P[ghosts])`` -- each boundary is a self-contained Q -> Q map,
+    applied Jacobi-style (all image reads before any ghost write).
     """
-    P = cfd.state2primitive(fluid, Q)
     touched = []
     for name, bc in bcs:
+        P = cfd.state2primitive(fluid, Q)
         impose_bc(lambda b, Pi: bc(Pi, b.normals), dom, name, P)
-        for b in dom.boundaries[name].values():
-            touched.append(b.ghost_indices)
-    g = np.unique(np.concatenate(touched)) if touched else np.zeros(0, np.int64)
-    Q[g] = cfd.primitive2state(fluid, P[g])
-    return g
+        g = np.unique(np.concatenate([b.ghost_indices for b in dom.boundaries[name].values()] or [np.zeros(0, np.int64)]))
+        Q[g] = cfd.primitive2state(fluid, P[g])
+        touched.append(g)
+    return np.unique(np.concatenate(touched)) if touched else np.zeros(0, np.int64)
