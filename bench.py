@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: cell-updates/s of (IB ghost update of every boundary + full Euler residual).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libibx, sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the restated reference path (NumPy oracle)
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d "C4"): 3-D sphere octree, box (-16)^3..16^3, block_size 8,
+growth_ratio 2, sphere radius 0.5 (analytic surface), finest cell width 32/2^10/8 inside Ball(0, r); r = 0.75
+gives 50.2 M cells on one GPU and is enlarged so that the cell count grows with the number of GPUs (weak
+scaling, ~50 M cells per GPU).  Inputs: the smooth synthetic state of SURVEY.md 8(d), seed 12345.
+One step = halo exchange + ghost update (wall, farfield) + halo exchange + residual on every rank.
+The working set (state 1 GB + residual 1.2 GB + scratch 1.2 GB per 50 M cells) is far larger than the 126 MB L2,
+so no explicit L2 flush is needed between timed iterations.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+F32 = np.float32
+
+H_FINE = 32.0 / 2 ** 10 / 8 * 1.01       # requested cell size: just above the level-10 cell width
+CELLS_PER_GPU = 50_000_000
+B_ALG = 4 * (2 * 5 + 1)                  # 44 B per cell-update: read Q, write R, write cfl
+B_GHOST = 4 * (5 + 5) + 8 * (4 + 4) + 4 * (3 + 1)   # 120 B per ghost
+
+
+def build_mesh(ib, radius, h=H_FINE):
+    return ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(h)),
+                   refinement_regions=[(ib.Ball([0, 0, 0], radius), F32(h))])
+
+
+def radius_for(ib, target_cells, h=H_FINE):
+    """Smallest refinement-ball radius (on a 1/64 grid) whose mesh has at least `target_cells` cells."""
+    if target_cells <= 50_300_000 and h == H_FINE:
+        return 0.75
+    lo, hi = 0.5, 4.0
+    for _ in range(12):
+        mid = round((lo + hi) / 2 * 64) / 64
+        if mid in (lo, hi):
+            break
+        if len(build_mesh(ib, mid, h)) >= target_cells:
+            hi = mid
+        else:
+            lo = mid
+    return hi
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def measured_peak_gbs():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference(cells_target, steps, warmup):
+    """The restated reference path (oracle: array-at-a-time operators, one task per partition like
+    ThreadTools.tmap) on a BOUNDED sample: the same sphere-octree recipe at a coarser size."""
+    import oracle
+    from oracle import cfd as ocfd, euler as oeuler
+    from immersedboundary_jl_b200 import synthetic
+    OM = oracle.mesher
+    cores = os.cpu_count() or 1
+    h = F32(0.25)
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    msh = OM.Mesh([-16, -16, -16], [32, 32, 32], ("wall", OM.AnalyticSphere([0, 0, 0], 0.5), h),
+                  refinement_regions=[(OM.Ball([0, 0, 0], cells_target), h)])
+    dom = oracle.domain.Domain(msh, max_partition_size=max(4096, len(msh) // max(cores, 1) + 1), hypercube_families=fams)
+    fl = ocfd.Fluid()
+    a = np.sqrt(1.4 * 283.0 * 288.15)
+    Pinf = np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)
+    bcs = [("wall", ocfd.FlowBC(fl, Pinf[:3] * np.array([1, 1, 0], F32), normal_flow=True)), ("farfield", ocfd.FlowBC(fl, Pinf))]
+    Q = synthetic.primitive2state_host(synthetic.euler_state(dom.centers))
+    R, cf = np.zeros_like(Q), np.zeros(len(Q), F32)
+    res = oeuler.euler_residual(fl)
+
+    def step():
+        oeuler.euler_ghost_update(dom, fl, Q, bcs)
+        dom(res, Q, R, cf, n_threads=cores)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": len(Q) * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"NumPy restatement of the reference operators (Julia cannot run here), same sphere-octree recipe at "
+                      f"h={float(h)} -> {len(Q)} cells in {len(dom.partitions)} partitions, {steps} evaluations, "
+                      f"{cores} threads (one task per partition, like tmap)",
+            "ms_per_step": dt / steps * 1e3, "cells": len(Q)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(1.5, max(1, min(args.steps, 5)), min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "cell-updates/s (Euler residual+IB)", "value": r["value"], "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "3-D sphere octree Euler (HLL + MUSCL + JST) + IB ghost update, bounded CPU sample",
+                       "cells": r["cells"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import immersedboundary_jl_b200 as ib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // world)))
+    ctx = ib.context(local_rank)
+    t_setup = time.perf_counter()
+    cells_target = args.cells if args.cells else CELLS_PER_GPU * world
+    h = 32.0 / 2 ** args.level / 8 * 1.01
+    radius = radius_for(ib, cells_target, h) if not args.radius else args.radius
+    msh = build_mesh(ib, radius, h)
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    gdom = ib.Domain(msh, max_partition_size=len(msh), hypercube_families=fams, build_partitions=False,
+                     build_surfaces=False, upload=False)
+    n_global = len(gdom)
+    if world > 1:
+        def gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        dom = gdom.shard(rank, world, all_gather_object=gather)
+        ident = np.zeros(128, np.uint8)
+        if rank == 0:
+            ib._lib.call("ibx_comm_unique_id", ib._lib.ptr(ident))
+        obj = [ident.tobytes()]
+        dist.broadcast_object_list(obj, src=0)
+        ident = np.frombuffer(obj[0], np.uint8).copy()
+        ib._lib.call("ibx_comm_init", ctx, rank, world, ib._lib.ptr(ident))
+        l2g = dom.shard_info["local_to_global"]
+        n_owned = dom.shard_info["n_owned"]
+        centers = gdom.cells()[0][l2g]
+        del gdom
+    else:
+        dom, n_owned = gdom, n_global
+        centers = dom.cells()[0]
+    dom.upload()
+    n_local = len(dom)
+    fluid = ib.Fluid()
+    a_inf = math.sqrt(1.4 * 283.0 * 288.15)
+    Pinf = np.array([101325.0, 288.15, 0.5 * a_inf, 0.0, 0.0], F32)
+    bcs = [("wall", ib.FlowBC(fluid, np.array([101325.0, 288.15, 0.0], F32), normal_flow=True)), ("farfield", ib.FlowBC(fluid, Pinf))]
+    Q_host = ib.pinned_empty((n_local, 5))
+    Q_host[...] = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(centers))
+    del centers
+    Q = ib.DeviceArray(n_local, 5, False).upload(Q_host)
+    R, cfl = ib.DeviceArray(n_local, 5, False), ib.DeviceArray(n_local, 1, True)
+    n_ghost = sum(b.nghost for bs in dom.boundaries.values() for b in bs.values())
+    setup_s = time.perf_counter() - t_setup
+
+    def step():
+        if world > 1:
+            dom.halo_exchange(Q)
+        ib.ghost_update_euler(dom, fluid, Q, bcs)
+        if world > 1:
+            dom.halo_exchange(Q)
+        ib.residual_euler(dom, fluid, Q, R, cfl)
+
+    def barrier():
+        ib.synchronize()
+        if world > 1:
+            dist.barrier()
+        ib.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ib.launch_count()
+    ib._lib.call("ibx_timer_start", ctx)
+    for _ in range(args.steps):
+        step()
+    ms = C.c_float()
+    ib._lib.call("ibx_timer_stop", ctx, C.byref(ms))
+    barrier()
+    launches = ib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ms.value
+    if world > 1:
+        import torch
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_global * args.steps / (ms_total * 1e-3)
+
+    # dominant kernel alone (CUDA events on the library's compute stream) for the roofline entry
+    reps = max(3, min(args.steps, 10))
+    ib._lib.call("ibx_timer_start", ctx)
+    for _ in range(reps):
+        ib.residual_euler(dom, fluid, Q, R, cfl)
+    ib._lib.call("ibx_timer_stop", ctx, C.byref(ms))
+    ms_res = ms.value / reps
+    peak, peak_kind = measured_peak_gbs()
+    alg_bytes = n_owned * B_ALG
+    achieved = alg_bytes / (ms_res * 1e-3) / 1e9
+
+    # end-to-end through the C ABI with HOST buffers (pinned): H2D(Q) + ghost + residual + D2H(R, cfl) per step
+    e2e = None
+    if world == 1:
+        R_host, c_host = ib.pinned_empty((n_local, 5)), ib.pinned_empty((n_local,))
+        del R, cfl
+        for _ in range(2):
+            ib.euler_step_host(dom, fluid, bcs, Q_host, R_host, c_host)
+        k = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            ib.euler_step_host(dom, fluid, bcs, Q_host, R_host, c_host)
+        dt = time.perf_counter() - t0
+        e2e = {"value": n_global * k / dt, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Q_host.nbytes),
+               "d2h_bytes_per_step": int(R_host.nbytes + c_host.nbytes), "ms_per_step": dt / k * 1e3, "steps": k,
+               "api": "ibx_euler_step_host (C ABI, pinned host buffers)"}
+    else:
+        e2e = {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "end-to-end host-buffer path is measured at N=1 only"}
+
+    if world > 1:
+        ib._lib.call("ibx_comm_finalize", ctx)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(1.5, 3, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": "cell-updates/s (Euler residual+IB)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C4: 3-D sphere octree Euler residual (MUSCL + JST sensor + HLL) + IB ghost update (wall, farfield)",
+                   "cells": n_global, "cells_per_gpu": n_owned, "ghost_cells_rank0": n_ghost, "blocks": msh.nblocks,
+                   "refinement_ball_radius": radius, "finest_level": args.level, "block_size": 8, "nv": 5, "partition": "contiguous block ranges, one per GPU",
+                   "l2": "working set >> 126 MB L2, no flush needed", "setup_s": round(setup_s, 1)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "ibx_residual_euler (k_prim + k_sensor + k_euler_flux)",
+                     "ms_per_launch": ms_res, "algorithmic_bytes_per_cell": B_ALG,
+                     "whole_step_achieved": (n_owned * B_ALG + n_ghost * B_GHOST) / (ms_step * 1e-3) / 1e9},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    import ctypes as C
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=0, help="override the target cell count (debugging)")
+    ap.add_argument("--radius", type=float, default=0.0, help="override the refinement-ball radius (debugging)")
+    ap.add_argument("--level", type=int, default=10, help="finest octree level (10 = the C4 workload; lower for smoke runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

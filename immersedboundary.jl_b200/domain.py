@@ -397,10 +397,14 @@ class Domain:
     on a machine without a GPU)."""
 
     def __init__(self, msh, max_partition_size=100_000, partition_skirt_depth=2, ghost_layer_ratio=F32(1.5),
-                 hypercube_families=(), build_partitions=True, build_surfaces=True, upload=True):
+                 hypercube_families=(), build_partitions=True, build_surfaces=True, upload=True, _handle=None):
         self.mesh = msh
         self._h = C.c_void_p()
         fams = list(hypercube_families)
+        if _handle is not None:
+            self._h = _handle
+            self._describe(max_partition_size, partition_skirt_depth, ghost_layer_ratio, fams)
+            return
         names = (C.c_char_p * max(len(fams), 1))(*[n.encode() for n, _ in fams])
         fptr = np.zeros(len(fams) + 1, dtype=np.int32)
         dims, fronts = [], []
@@ -414,6 +418,11 @@ class Domain:
         call("ibx_domain_build", msh._h, int(max_partition_size), int(partition_skirt_depth), float(ghost_layer_ratio),
              len(fams), names, ptr(fptr), ptr(dims), ptr(fronts), int(build_partitions), int(build_surfaces),
              C.byref(self._h))
+        self._describe(max_partition_size, partition_skirt_depth, ghost_layer_ratio, fams)
+        if upload:
+            self.upload()
+
+    def _describe(self, max_partition_size, partition_skirt_depth, ghost_layer_ratio, fams):
         nd, nc, nf, npart, nb, ns = C.c_int(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int(), C.c_int()
         call("ibx_domain_info", self._h, C.byref(nd), C.byref(nc), C.byref(nf), C.byref(npart), C.byref(nb), C.byref(ns))
         self.ndims, self.ncells, self.nfaces = nd.value, nc.value, nf.value
@@ -438,8 +447,52 @@ class Domain:
                                           ghost_layer_ratio=ghost_layer_ratio,
                                           hypercube_families=[(n, list(f)) for n, f in fams])
         self.uploaded = False
-        if upload:
-            self.upload()
+        self.shard_info = None
+
+    # -- multi-GPU: rank-local shard
+    def shard(self, rank, nranks, all_gather_object=None):
+        """Rank-local domain: the rank's contiguous block range + the skirt / image-donor cells it reads.
+
+        ``all_gather_object(obj) -> [obj_rank0, ...]`` moves the halo request lists between ranks (e.g.
+        ``torch.distributed.all_gather_object``); with ``nranks == 1`` it is not needed."""
+        out = C.c_void_p()
+        call("ibx_domain_shard", self._h, int(rank), int(nranks), C.byref(out))
+        loc = Domain(self.mesh, _handle=out, **{k: v for k, v in self.reconstruction_kwargs.items()})
+        no, nh, st = C.c_int64(), C.c_int64(), C.c_int64()
+        call("ibx_shard_info", loc._h, C.byref(no), C.byref(nh), C.byref(st))
+        l2g = np.zeros(no.value + nh.value, dtype=I32)
+        call("ibx_shard_tables", loc._h, ptr(l2g))
+        sc, rc = np.zeros(nranks, np.int64), np.zeros(nranks, np.int64)
+        call("ibx_halo_sizes", loc._h, nranks, ptr(sc), ptr(rc))
+        requests = {}
+        for peer in range(nranks):
+            r = np.zeros(rc[peer], dtype=I32)
+            call("ibx_halo_lists", loc._h, peer, None, ptr(r))
+            requests[peer] = l2g[r]          # global ids, in this rank's unpack order
+        loc.shard_info = dict(rank=rank, nranks=nranks, n_owned=no.value, n_halo=nh.value, owned_start=st.value,
+                              local_to_global=l2g, requests=requests)
+        if nranks > 1:
+            everyone = all_gather_object(requests)
+            for peer in range(nranks):
+                ids = np.ascontiguousarray(everyone[peer][rank], dtype=I32)
+                call("ibx_shard_set_send", loc._h, peer, len(ids), ptr(ids))
+        return loc
+
+    def halo_exchange(self, a):
+        """Post and complete the exchange of the halo rows of device array ``a`` (n_owned + n_halo rows)."""
+        call("ibx_halo_begin", context(), self._h, a.h)
+        call("ibx_halo_end", context(), self._h, a.h)
+
+    def send_lists(self):
+        out = {}
+        n = self.shard_info["nranks"]
+        sc, rc = np.zeros(n, np.int64), np.zeros(n, np.int64)
+        call("ibx_halo_sizes", self._h, n, ptr(sc), ptr(rc))
+        for peer in range(n):
+            s_, r_ = np.zeros(sc[peer], dtype=I32), np.zeros(rc[peer], dtype=I32)
+            call("ibx_halo_lists", self._h, peer, ptr(s_), ptr(r_))
+            out[peer] = (s_, r_)
+        return out
 
     def upload(self):
         if not self.uploaded:

@@ -1,0 +1,105 @@
+"""Multi-rank host logic on CPU: world_size-2 gloo processes build their shards, trade halo request lists with
+torch.distributed, and run the pack -> send/recv -> unpack exchange on CPU tensors with the library's own lists."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F32 = np.float32
+
+
+def _build(ib):
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    m = ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(0.12)),
+                refinement_regions=[(ib.Ball([0, 0, 0], 0.9), F32(0.24))])
+    return m, fams, ib.Domain(m, hypercube_families=fams, build_partitions=False, upload=False)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import immersedboundary_jl_b200 as ib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _, _, g = _build(ib)
+
+        def gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        loc = g.shard(rank, world, all_gather_object=gather)
+        info = loc.shard_info
+        l2g = info["local_to_global"]
+        n_local = info["n_owned"] + info["n_halo"]
+        f = lambda gid: np.stack([np.sin(gid * 0.37), gid * 1.0], axis=1).astype(F32)  # a field known by global id
+        A = np.zeros((n_local, 2), F32)
+        A[: info["n_owned"]] = f(l2g[: info["n_owned"]].astype(np.float64))
+        lists = loc.send_lists()
+        reqs = []
+        recv_bufs = {}
+        for peer in range(world):
+            s_, r_ = lists[peer]
+            if len(s_):
+                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(A[s_])), peer))
+            if len(r_):
+                recv_bufs[peer] = torch.zeros((len(r_), 2), dtype=torch.float32)
+                reqs.append(dist.irecv(recv_bufs[peer], peer))
+        for r in reqs:
+            r.wait()
+        for peer, buf in recv_bufs.items():
+            A[lists[peer][1]] = buf.numpy()
+        needed = np.concatenate([lists[p][1] for p in range(world)])
+        ok = np.array_equal(A[needed], f(l2g[needed].astype(np.float64)))
+        q.put((rank, ok, info["n_owned"], info["owned_start"], sorted(l2g[needed].tolist())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_halo_exchange_gloo(ib, oracle):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m, fams, g = _build(ib)
+    assert sum(r[2] for r in res) == len(g) and res[0][3] == 0 and res[1][3] == res[0][2]
+    assert all(r[1] for r in res)
+    # the requested cells are exactly the reference's 2-deep skirt of the owned range (+ image donors)
+    OM = oracle.mesher
+    om = OM.Mesh([-2, -2, -2], [4, 4, 4], ("wall", OM.AnalyticSphere([0, 0, 0], 0.5), F32(0.12)),
+                 refinement_regions=[(OM.Ball([0, 0, 0], 0.9), F32(0.24))])
+    od = oracle.domain.Domain(om, hypercube_families=fams)
+    for rank, _, n_owned, start, needed in res:
+        image = np.arange(start, start + n_owned, dtype=np.int64)
+        part = oracle.domain.build_partition(1, image, od.faces, od.c2f_ptr, od.c2f_idx, od.centers, od.widths, 2)
+        skirt = set(np.setdiff1d(part.domain, image).tolist())
+        donors = set()
+        for bs in od.boundaries.values():
+            for b in bs.values():
+                own = (b.ghost_indices >= start) & (b.ghost_indices < start + n_owned)
+                ptr, idx, _ = b.image_interpolator.to_csr()
+                for gi in np.flatnonzero(own):
+                    donors.update(b.image_domain[idx[ptr[gi]:ptr[gi + 1]]].tolist())
+        donors = {d for d in donors if not (start <= d < start + n_owned)}
+        assert set(needed) == skirt | donors
+
+
+def test_single_rank_shard_is_identity(ib):
+    _, _, g = _build(ib)
+    loc = g.shard(0, 1)
+    assert loc.shard_info["n_owned"] == len(g) and loc.shard_info["n_halo"] == 0
+    assert np.array_equal(loc.shard_info["local_to_global"], np.arange(len(g)))
+    assert np.array_equal(loc.block_faces(), g.block_faces())
+    for name in g.boundaries:
+        assert sum(b.nghost for b in loc.boundaries[name].values()) == sum(b.nghost for b in g.boundaries[name].values())
