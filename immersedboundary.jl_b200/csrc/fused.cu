@@ -11,8 +11,16 @@
 // averaged with weight 1/len.  Image-cell results do not depend on the partitioning because the skirt
 // is 2 deep, so this equals the reference's per-partition evaluation followed by its scatter.
 #include "device.cuh"
+#include "physics.cuh"
 
 using namespace ibx;
+using namespace ibxk;
+
+namespace ibx {
+bool tile_supported(const ibx_domain& D);
+int residual_euler_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,
+                         float* R, float* cfl);
+}
 
 namespace {
 
@@ -112,10 +120,6 @@ __device__ __forceinline__ Nbr<ND> neighbors(const Topo& T, int64_t cell, int64_
   return out;
 }
 
-__device__ __forceinline__ float clampT(float T) { return fmaxf(T, 10.0f); }
-__device__ __forceinline__ float sgn(float x) { return (float)((x > 0.0f) - (x < 0.0f)); }
-__device__ __forceinline__ float face_interp(float uo, float un, float ho, float hn) { return (uo * hn + un * ho) / (hn + ho); }
-
 // ------------------------------------------------------------------ pass 1a: Q -> P
 template <int ND>
 __global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n) {
@@ -206,104 +210,6 @@ __device__ __forceinline__ void cell_grad(const Topo& T, const float* __restrict
   for (int v = 0; v < NV; ++v) g[v] = (m[1][v] - m[0][v]) / hc;
 }
 
-template <int NV>
-__device__ __forceinline__ void muscl_face(const float* uo, const float* un, const float* duo, const float* dun, float ho,
-                                           float hn, float Do, float Dn, bool use_D, bool high_order, float* uL, float* uR) {
-  float down = ho / 2.0f, dnei = hn / 2.0f;
-  float Df = fmaxf(fmaxf(Do, Dn), 1e-7f);
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    float gf = (un[v] - uo[v]) / (down + dnei);
-    float gu = (2.0f * duo[v] - gf) * down;
-    float Du = (2.0f * dun[v] - gf) * dnei;
-    float s = fminf(fabsf(Du), fabsf(gu)) * (sgn(Du) + sgn(gu)) / 2.0f;
-    float l = uo[v] + s, r = un[v] - s;
-    if (use_D) {
-      float uf = (uo[v] * dnei + un[v] * down) / (down + dnei);
-      if (high_order) uf = uf + (duo[v] * down - dun[v] * dnei) / 8.0f;
-      l = l * Df + (1.0f - Df) * uf;
-      r = r * Df + (1.0f - Df) * uf;
-    }
-    uL[v] = l;
-    uR[v] = r;
-  }
-}
-
-template <int ND>
-__device__ __forceinline__ void p2s(ibx_fluid f, const float* P, float* Q) {
-  float T = clampT(P[1]);
-  float k = P[2] * P[2];
-#pragma unroll
-  for (int d = 1; d < ND; ++d) k = k + P[2 + d] * P[2 + d];
-  k = k / 2.0f;
-  float rho = P[0] / (f.R * T);
-  Q[0] = rho;
-  Q[1] = rho * (f.R / (f.gamma - 1.0f) * T + k);
-#pragma unroll
-  for (int d = 0; d < ND; ++d) Q[2 + d] = rho * P[2 + d];
-}
-
-template <int ND>
-__device__ __forceinline__ void s2p(ibx_fluid f, const float* Q, float* P) {
-  float rho = Q[0];
-  float k = 0.0f;
-#pragma unroll
-  for (int d = 0; d < ND; ++d) {
-    P[2 + d] = Q[2 + d] / rho;
-    k = d == 0 ? P[2] * P[2] : k + P[2 + d] * P[2 + d];
-  }
-  k = k / 2.0f;
-  float p = (f.gamma - 1.0f) * (Q[1] - rho * k);
-  P[0] = p;
-  P[1] = clampT(p / (rho * f.R));
-}
-
-// HLL flux of src/cfd.jl:459-508 (float32 throughout; the reference's accidental Float64 promotion of the
-// last line is within the 1e-5 parity tolerance)
-template <int ND>
-__device__ __forceinline__ void hll_flux(ibx_fluid f, const float* pl, const float* pr, int dim, float* F) {
-  constexpr int NV = ND + 2;
-  float ql[NV], qr[NV];
-  p2s<ND>(f, pl, ql);
-  p2s<ND>(f, pr, qr);
-  float gr = f.gamma * f.R;
-  float uL = pl[2 + dim], uR = pr[2 + dim];
-  float aL = sqrtf(gr * clampT(pl[1])), aR = sqrtf(gr * clampT(pr[1]));
-  float SR = fminf(uR - aR, 0.0f), SL = fmaxf(uL + aL, 0.0f);
-  float inv = 1.0f / (SL - SR);
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    float l = ql[v], r = qr[v];
-    if (v == 1) { l += pl[0]; r += pr[0]; }
-    l *= uL;
-    r *= uR;
-    if (v == 2 + dim) { l += pl[0]; r += pr[0]; }
-    F[v] = (SL * l - SR * r + SR * SL * (qr[v] - ql[v])) * inv;
-  }
-}
-
-// sensor-Rusanov flux of src/cfd.jl:516-554 with nuL = nuR = nu
-template <int ND>
-__device__ __forceinline__ void rusanov_flux(ibx_fluid f, const float* pl, const float* pr, float nu, int dim, float* F) {
-  constexpr int NV = ND + 2;
-  float ul[NV], ur[NV], pm[NV];
-  p2s<ND>(f, pl, ul);
-  p2s<ND>(f, pr, ur);
-  ul[1] += pl[0];
-  ur[1] += pr[0];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) pm[v] = (pl[v] + pr[v]) / 2.0f;
-  float u = pm[2 + dim];
-  float a = sqrtf(f.gamma * f.R * clampT(pm[1]));
-  float diss = nu * (a + fabsf(u)) / 2.0f;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    float fv = (ul[v] + ur[v]) * u / 2.0f;
-    if (v == 2 + dim) fv += pm[0];
-    F[v] = fv + (ul[v] - ur[v]) * diss;
-  }
-}
-
 template <int ND>
 __global__ void __launch_bounds__(TB) k_euler_flux(Topo T, ibx_fluid f, int flux_kind, const float* __restrict__ P,
                                                    const float* __restrict__ D, float* __restrict__ R, float* __restrict__ cfl) {
@@ -325,14 +231,16 @@ __global__ void __launch_bounds__(TB) k_euler_flux(Topo T, ibx_fluid f, int flux
       float hc = T.h[b * ND + d];
       float gc[NV];
       cell_grad<ND, NV>(T, P, cell, d, gc);
-      float msum[2][NV], csum[2];
+      double msum[2][NV];
+      float csum[2];
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
         Nbr<ND> nb = neighbors<ND>(T, cell, b, ii, d, side);
         float w = 1.0f / (float)nb.cnt;
         for (int k = 0; k < nb.cnt; ++k) {
           int64_t n = nb.cell[k];
-          float pn[NV], gn[NV], F[NV], pl[NV], pr[NV];
+          float pn[NV], gn[NV], pl[NV], pr[NV];
+          double F[NV];
           float Dn;
           if (n == cell) {  // box face
 #pragma unroll
@@ -358,17 +266,33 @@ __global__ void __launch_bounds__(TB) k_euler_flux(Topo T, ibx_fluid f, int flux
           if (flux_kind == 0) {
             hll_flux<ND>(f, pl, pr, d, F);
           } else {
+            float Ff[NV];
             float nu = side ? face_interp(Dc, Dn, hc, nb.h) : face_interp(Dn, Dc, nb.h, hc);
-            rusanov_flux<ND>(f, pl, pr, nu, d, F);
+            rusanov_flux<ND>(f, pl, pr, nu, d, Ff);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) F[v] = (double)Ff[v];
           }
           float ct = (fabsf(uf) + af) * w;
           csum[side] = k == 0 ? ct : csum[side] + ct;
+          if (flux_kind == 0) {   // Float64 Green-Gauss sums, like the reference after its HLL promotion
 #pragma unroll
-          for (int v = 0; v < NV; ++v) msum[side][v] = k == 0 ? F[v] * w : msum[side][v] + F[v] * w;
+            for (int v = 0; v < NV; ++v) msum[side][v] = k == 0 ? F[v] * (double)w : msum[side][v] + F[v] * (double)w;
+          } else {                // the sensor flux stays Float32 end to end
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              float t = (float)F[v] * w;
+              msum[side][v] = k == 0 ? (double)t : (double)((float)msum[side][v] + t);
+            }
+          }
         }
       }
+      if (flux_kind == 0) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) res[v] = res[v] - (msum[1][v] - msum[0][v]) / hc;
+        for (int v = 0; v < NV; ++v) res[v] = (float)((double)res[v] - (msum[1][v] - msum[0][v]) / (double)hc);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) res[v] = res[v] - ((float)msum[1][v] - (float)msum[0][v]) / hc;
+      }
       cf = cf + (csum[1] + csum[0]) / hc;
     }
 #pragma unroll
@@ -560,6 +484,10 @@ int ibx_residual_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_ki
   if (!scratch) return fail(IBX_ERR_CUDA, "ibx_residual_euler: out of device memory for the primitive/sensor scratch");
   float* P = scratch;
   float* S = scratch + N * nv;
+  // tile kernels (one CTA per block, shared-memory staging) for power-of-two blocks; IBX_GENERIC=1 forces the
+  // gather kernels (kept as the fallback for other block sizes and as a cross-check)
+  const bool force_generic = getenv("IBX_GENERIC") != nullptr;
+  if (tile_supported(D) && !force_generic) return residual_euler_tiles(c, D, f, flux_kind, Q.p, P, S, R.p, CF.p);
   Topo T = make_topo(D);
   int g = fused_grid(c, N);
   if (D.nd == 2) {

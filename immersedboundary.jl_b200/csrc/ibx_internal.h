@@ -198,6 +198,9 @@ struct ibx_domain {
   int device = -1;
   ibx::BlockFace* d_block_faces = nullptr;
   float* d_block_h = nullptr;
+  // block work lists of the tile kernels: blocks without / with a finer neighbour; all local vs owned only
+  int32_t *d_blk_all_plain = nullptr, *d_blk_all_finer = nullptr, *d_blk_own_plain = nullptr, *d_blk_own_finer = nullptr;
+  int n_all_plain = 0, n_all_finer = 0, n_own_plain = 0, n_own_finer = 0;
   ibx::Shard shard;
   ~ibx_domain();
 };

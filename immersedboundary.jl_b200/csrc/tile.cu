@@ -1,0 +1,525 @@
+// Tile kernels of the fused Euler residual: one CTA per octree block, everything staged in shared memory.
+//
+// Layout in HBM: every field is column-major N x nv, i.e. one contiguous plane per variable, and cell ids are
+// block-major with the first dimension fastest inside a block (src/mesher.jl:1079-1092).  A block's BS^ND cells of
+// one variable are therefore ONE contiguous run (2 KB for 8^3 floats): own cells load fully coalesced; halo cells
+// come in runs of BS along x.
+//
+// Per block the CTA stages its own cells plus, for each of the 2*ND block faces, the first TWO cell layers of the
+// neighbouring block(s) at THEIR resolution (same level: BS^(ND-1) x 2, coarser: (BS/2)^(ND-1) x 2, finer:
+// (2 BS)^(ND-1) x 2).  That is the reference's 2-deep skirt (src/ImmersedBoundary.jl:610-619) of a partition whose
+// image is the block, restricted to what a dimension-split residual reads: the gradient of a neighbour cell along
+// the face normal needs (a) this block's cells and (b) the neighbour's second layer -- both staged.  The JST sensor
+// also needs lateral neighbours of the neighbour cells, so it is produced by its own tile pass (k_tile_sensor) and
+// staged here as a sixth field.
+// Work per dimension: gradients -> face fluxes (each face ONCE: MUSCL + HLL) -> divergence; three barriers.
+#include "device.cuh"
+#include "physics.cuh"
+
+using namespace ibx;
+using namespace ibxk;
+
+namespace {
+
+template <int ND, int BS, bool FINER>
+struct Cfg {
+  static constexpr int NV = ND + 2;
+  static constexpr int CPB = ND == 3 ? BS * BS * BS : BS * BS;
+  static constexpr int FACE = ND == 3 ? BS * BS : BS;
+  static constexpr int MAXL1 = FINER ? FACE * (ND == 3 ? 4 : 2) : FACE;  // cells per halo layer == faces per block face
+  static constexpr int NFACES = 2 * ND;
+  static constexpr int NS = CPB + NFACES * 2 * MAXL1;                    // staged cells (own + 2-layer halos)
+  static constexpr int NG = CPB + 2 * MAXL1;                             // gradient / flux slots per dimension
+  static constexpr int NT = CPB >= 512 ? 256 : (CPB >= 64 ? 64 : 32);
+  static constexpr int CPT = (CPB + NT - 1) / NT;
+  // doubles first (8-byte alignment): face fluxes [NV][NG]; then floats: P [NV][NS], D [NS], gradient [NV][NG], CFL term [NG]
+  static constexpr size_t SMEM_FLUX = sizeof(double) * (size_t)NV * NG + sizeof(float) * ((size_t)(NV + 1) * NS + (size_t)(NV + 1) * NG);
+  static constexpr size_t SMEM_SENSOR = sizeof(float) * ((size_t)CPB + NFACES * MAXL1);
+};
+
+struct FaceInfo {
+  int kind, n1, n2, base, nfaces;
+  float hn;
+  int nb[4];
+  int sub1, sub2;
+};
+
+__device__ __forceinline__ int T1(int d) { return d == 0 ? 1 : 0; }
+__device__ __forceinline__ int T2(int d) { return d == 2 ? 1 : 2; }
+
+template <int ND, int BS>
+__device__ __forceinline__ int compose(int d, int cn, int c1, int c2) {
+  int idx[3] = {0, 0, 0};
+  idx[d] = cn;
+  idx[T1(d)] = c1;
+  if (ND == 3) idx[T2(d)] = c2;
+  return idx[0] + BS * (idx[1] + BS * idx[2]);
+}
+
+template <int ND, int BS>
+__device__ __forceinline__ void split(int l, int (&ii)[3]) {
+  ii[0] = l % BS;
+  ii[1] = (l / BS) % BS;
+  ii[2] = ND == 3 ? l / (BS * BS) : 0;
+}
+
+// base: first slot of this face's halo area; layers: 1 (sensor) or 2 (flux)
+template <int ND, int BS>
+__device__ __forceinline__ void fill_face_info(FaceInfo& fi, const BlockFace& bf, int base, float h) {
+  fi.kind = bf.kind >= 1 && bf.kind <= 3 ? bf.kind : 0;
+  fi.sub1 = bf.sub[0];
+  fi.sub2 = bf.sub[1];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) fi.nb[q] = bf.nb[q];
+  int n = fi.kind == 1 ? BS : (fi.kind == 2 ? BS / 2 : (fi.kind == 3 ? 2 * BS : 0));
+  fi.n1 = n;
+  fi.n2 = ND == 3 ? n : (n ? 1 : 0);
+  fi.hn = fi.kind == 2 ? h * 2.0f : (fi.kind == 3 ? h * 0.5f : h);
+  fi.base = base;
+  fi.nfaces = fi.kind == 3 ? fi.n1 * fi.n2 : (ND == 3 ? BS * BS : BS);
+}
+
+// global cell id of halo cell (j1, j2, layer) of face (d, side)
+template <int ND, int BS>
+__device__ __forceinline__ int64_t halo_cell(const FaceInfo& fi, int d, int side, int j1, int j2, int layer, int64_t cpb) {
+  int jn = side ? layer : BS - 1 - layer;
+  int64_t nb;
+  int J1 = j1, J2 = j2;
+  if (fi.kind == 1) {
+    nb = fi.nb[0];
+  } else if (fi.kind == 2) {
+    nb = fi.nb[0];
+    J1 = j1 + fi.sub1 * (BS / 2);
+    J2 = ND == 3 ? j2 + fi.sub2 * (BS / 2) : 0;
+  } else {
+    int q1 = j1 / BS, q2 = ND == 3 ? j2 / BS : 0;
+    nb = fi.nb[q1 + 2 * q2];
+    J1 = j1 % BS;
+    J2 = ND == 3 ? j2 % BS : 0;
+  }
+  return nb * cpb + compose<ND, BS>(d, jn, J1, J2);
+}
+
+// layer-0 halo slots (relative to fi.base) of the cells facing own cell (a1, a2); ascending cell id
+template <int ND, int BS>
+__device__ __forceinline__ int own_to_halo(const FaceInfo& fi, int a1, int a2, int (&slot)[4]) {
+  if (fi.kind == 1) {
+    slot[0] = a2 * fi.n1 + a1;
+    return 1;
+  }
+  if (fi.kind == 2) {
+    slot[0] = (a2 >> 1) * fi.n1 + (a1 >> 1);
+    return 1;
+  }
+  constexpr int CNT = ND == 3 ? 4 : 2;
+#pragma unroll
+  for (int q = 0; q < CNT; ++q) slot[q] = (ND == 3 ? (2 * a2 + (q >> 1)) * fi.n1 : 0) + 2 * a1 + (q & 1);
+  return CNT;
+}
+
+// ------------------------------------------------------------------------------------------ sensor pass
+// D = JST_sensor(part, p) with dim = 0 (src/ImmersedBoundary.jl:1077-1097) for the cells of one block
+template <int ND, int BS, bool FINER>
+__global__ void __launch_bounds__(Cfg<ND, BS, FINER>::NT)
+k_tile_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
+              const float* __restrict__ p, float* __restrict__ D) {
+  using C = Cfg<ND, BS, FINER>;
+  extern __shared__ float smem[];
+  __shared__ FaceInfo fi[C::NFACES];
+  float* sp = smem;  // [CPB + NFACES * MAXL1]
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  if (tid < C::NFACES) fill_face_info<ND, BS>(fi[tid], faces[b * C::NFACES + tid], C::CPB + tid * C::MAXL1, 1.0f);
+  __syncthreads();
+  const int64_t cell0 = b * C::CPB;
+  for (int l = tid; l < C::CPB; l += C::NT) sp[l] = p[cell0 + l];
+#pragma unroll
+  for (int f = 0; f < C::NFACES; ++f) {
+    const FaceInfo& F = fi[f];
+    if (F.kind == 0) continue;
+    int d = f >> 1, side = f & 1, n = F.n1 * F.n2;
+    for (int k = tid; k < n; k += C::NT) sp[F.base + k] = p[halo_cell<ND, BS>(F, d, side, k % F.n1, k / F.n1, 0, C::CPB)];
+  }
+  __syncthreads();
+  float h[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) h[d] = bh[b * ND + d];
+  for (int l = tid; l < C::CPB; l += C::NT) {
+    int ii[3];
+    split<ND, BS>(l, ii);
+    float pc = sp[l], nu = 1e-7f;
+    int stride = 1;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float g[2], a[2];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        float accg = 0.0f, acca = 0.0f;
+        bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+        if (inner) {
+          float fd = side ? sp[l + stride] - pc : pc - sp[l - stride];  // p_neighbour - p_owner
+          accg = fd;
+          acca = fabsf(fd);
+        } else {
+          const FaceInfo& F = fi[2 * d + side];
+          if (F.kind != 0) {  // box face: owner == neighbour, difference 0
+            int slot[4];
+            int cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
+            float w = 1.0f / (float)cnt;
+            for (int q = 0; q < cnt; ++q) {
+              float pn = sp[F.base + slot[q]];
+              float fd = side ? pn - pc : pc - pn;
+              accg = q == 0 ? fd * w : accg + fd * w;
+              acca = q == 0 ? fabsf(fd) * w : acca + fabsf(fd) * w;
+            }
+          }
+        }
+        g[side] = accg;
+        a[side] = acca;
+      }
+      float gg = (g[1] - g[0]) / h[d], ugg = (a[1] + a[0]) / h[d];
+      nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ugg));
+      stride *= BS;
+    }
+    D[cell0 + l] = nu;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ flux pass
+template <int ND, int BS, bool FINER>
+__global__ void __launch_bounds__(Cfg<ND, BS, FINER>::NT)
+k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
+            int64_t N, ibx_fluid fl, int flux_kind, const float* __restrict__ P, const float* __restrict__ Dg,
+            float* __restrict__ R, float* __restrict__ cfl) {
+  using C = Cfg<ND, BS, FINER>;
+  constexpr int NV = C::NV, CPB = C::CPB, NT = C::NT, NS = C::NS, NG = C::NG, MAXL1 = C::MAXL1;
+  extern __shared__ double smem_d[];
+  __shared__ FaceInfo fi[C::NFACES];
+  double* sF = smem_d;              // [NV][NG] face fluxes of the current dimension (Float64, see hll_flux)
+  float* sP = (float*)(sF + NV * NG);  // [NV][NS] primitives
+  float* sD = sP + NV * NS;         // [NS]     sensor
+  float* sG = sD + NS;              // [NV][NG] gradient along the current dimension
+  float* sC = sG + NV * NG;         // [NG]     CFL term of each face
+  __shared__ float h[3];
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  if (tid < C::NFACES) fill_face_info<ND, BS>(fi[tid], faces[b * C::NFACES + tid], CPB + tid * 2 * MAXL1, bh[b * ND + (tid >> 1)]);
+  if (tid < ND) h[tid] = bh[b * ND + tid];
+  __syncthreads();
+  // ---- stage own cells (coalesced runs of CPB floats per variable) and the 2-layer halos
+  const int64_t cell0 = b * CPB;
+  for (int l = tid; l < CPB; l += NT) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sP[v * NS + l] = P[(int64_t)v * N + cell0 + l];
+    sD[l] = Dg[cell0 + l];
+  }
+#pragma unroll
+  for (int f = 0; f < C::NFACES; ++f) {
+    const FaceInfo& F = fi[f];
+    if (F.kind == 0) continue;
+    int d = f >> 1, side = f & 1, n1n2 = F.n1 * F.n2;
+    for (int k = tid; k < 2 * n1n2; k += NT) {
+      int layer = k / n1n2, r = k - layer * n1n2;
+      int64_t c = halo_cell<ND, BS>(F, d, side, r % F.n1, r / F.n1, layer, CPB);
+      int s = F.base + k;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sP[v * NS + s] = P[(int64_t)v * N + c];
+      sD[s] = Dg[c];
+    }
+  }
+  __syncthreads();
+
+  float res[C::CPT][NV], cf[C::CPT];
+#pragma unroll
+  for (int q = 0; q < C::CPT; ++q) {
+    cf[q] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) res[q][v] = 0.0f;
+  }
+  const float gr = fl.gamma * fl.R;
+
+  int stride = 1;
+#pragma unroll 1
+  for (int d = 0; d < ND; ++d) {
+    const float hd = h[d];
+    const FaceInfo& FL = fi[2 * d];
+    const FaceInfo& FH = fi[2 * d + 1];
+    const int nl = FL.kind ? FL.n1 * FL.n2 : 0, nh = FH.kind ? FH.n1 * FH.n2 : 0;
+    // ---- (1) Green-Gauss gradient along d: own cells, then layer-0 halo cells of the two faces normal to d
+    for (int it = tid; it < CPB + nl + nh; it += NT) {
+      float m[2][NV];
+      float hc;
+      int gslot;
+      if (it < CPB) {
+        const int l = it;
+        int ii[3];
+        split<ND, BS>(l, ii);
+        hc = hd;
+        gslot = l;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+          if (inner) {
+            int n = side ? l + stride : l - stride;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) m[side][v] = face_interp(sP[v * NS + l], sP[v * NS + n], hd, hd);
+          } else {
+            const FaceInfo& F = side ? FH : FL;
+            if (F.kind == 0) {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) m[side][v] = face_interp(sP[v * NS + l], sP[v * NS + l], hd, hd);
+            } else {
+              int slot[4];
+              int cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
+              float w = 1.0f / (float)cnt;
+              for (int q = 0; q < cnt; ++q) {
+                int n = F.base + slot[q];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                  float fv = face_interp(sP[v * NS + l], sP[v * NS + n], hd, F.hn);
+                  m[side][v] = q == 0 ? fv * w : m[side][v] + fv * w;
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sG[v * NG + gslot] = (m[1][v] - m[0][v]) / hc;
+      } else {
+        // halo cell n in layer 0 of face (d, side): far side = its layer-1 twin, near side = own cells
+        int side = it - CPB >= nl ? 1 : 0;
+        const FaceInfo& F = side ? FH : FL;
+        int r = it - CPB - (side ? nl : 0);
+        int j1 = r % F.n1, j2 = r / F.n1;
+        int n = F.base + r, far = n + F.n1 * F.n2;
+        hc = F.hn;
+        gslot = CPB + side * MAXL1 + r;
+        int bnd = side ? BS - 1 : 0;
+        float nearv[NV], farv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) farv[v] = face_interp(sP[v * NS + n], sP[v * NS + far], hc, hc);
+        if (F.kind == 1) {
+          int o = compose<ND, BS>(d, bnd, j1, j2);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+        } else if (F.kind == 3) {
+          int o = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+        } else {  // coarser halo cell: 2^(ND-1) own fine cells face it
+          constexpr int CNT = ND == 3 ? 4 : 2;
+          const float w = 1.0f / (float)CNT;
+#pragma unroll
+          for (int q = 0; q < CNT; ++q) {
+            int o = compose<ND, BS>(d, bnd, 2 * j1 + (q & 1), 2 * j2 + (q >> 1));
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              float fv = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+              nearv[v] = q == 0 ? fv * w : nearv[v] + fv * w;
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sG[v * NG + gslot] = side ? (farv[v] - nearv[v]) / hc : (nearv[v] - farv[v]) / hc;
+      }
+    }
+    __syncthreads();
+    // ---- (2) face fluxes along d, each face once: internal faces (slot = owner cell), low face, high face
+    const int nfl = FL.nfaces, nfh = FH.nfaces;
+    for (int it = tid; it < CPB + nfl + nfh; it += NT) {
+      int so, sn, go, gn, fslot;  // staged-cell slots and gradient slots of owner / neighbour
+      float ho, hn;
+      if (it < CPB) {
+        int ii[3];
+        split<ND, BS>(it, ii);
+        if (ii[d] == BS - 1) continue;
+        so = it; sn = it + stride; go = so; gn = sn; ho = hd; hn = hd; fslot = it;
+      } else {
+        int side = it - CPB >= nfl ? 1 : 0;
+        const FaceInfo& F = side ? FH : FL;
+        int k = it - CPB - (side ? nfl : 0);
+        int bnd = side ? BS - 1 : 0;
+        int own, hs, hg;
+        float hh = F.hn;
+        if (F.kind == 3) {
+          int j1 = k % F.n1, j2 = k / F.n1;
+          own = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
+          hs = F.base + k;
+          hg = CPB + side * MAXL1 + k;
+        } else {
+          int a1 = k % BS, a2 = k / BS;
+          own = compose<ND, BS>(d, bnd, a1, a2);
+          if (F.kind == 0) { hs = own; hg = own; hh = hd; }
+          else {
+            int r = F.kind == 1 ? k : (a2 >> 1) * F.n1 + (a1 >> 1);
+            hs = F.base + r;
+            hg = CPB + side * MAXL1 + r;
+          }
+        }
+        if (side) { so = own; go = own; ho = hd; sn = hs; gn = hg; hn = hh; }
+        else      { so = hs; go = hg; ho = hh; sn = own; gn = own; hn = hd; }
+        fslot = CPB + side * MAXL1 + k;
+      }
+      float po[NV], pn[NV], g0[NV], g1[NV], pl[NV], pr[NV];
+      double F_[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        po[v] = sP[v * NS + so];
+        pn[v] = sP[v * NS + sn];
+        g0[v] = sG[v * NG + go];
+        g1[v] = sG[v * NG + gn];
+      }
+      float Do = sD[so], Dn = sD[sn];
+      muscl_face<NV>(po, pn, g0, g1, ho, hn, Do, Dn, true, false, pl, pr);
+      if (flux_kind == 0) {
+        hll_flux<ND>(fl, pl, pr, d, F_);
+      } else {
+        float Ff[NV];
+        rusanov_flux<ND>(fl, pl, pr, face_interp(Do, Dn, ho, hn), d, Ff);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) F_[v] = (double)Ff[v];
+      }
+      float ao = sqrtf(gr * clampT(po[1])), an = sqrtf(gr * clampT(pn[1]));
+      float ct = fabsf(face_interp(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), ho, hn)) + face_interp(ao, an, ho, hn);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sF[v * NG + fslot] = F_[v];
+      sC[fslot] = ct;
+    }
+    __syncthreads();
+    // ---- (3) divergence: R -= (mean_high - mean_low) / h, cfl += (c_high + c_low) / h
+#pragma unroll
+    for (int q = 0; q < C::CPT; ++q) {
+      int l = tid + q * NT;
+      if (l >= CPB) break;
+      int ii[3];
+      split<ND, BS>(l, ii);
+      double mh[NV], ml[NV];
+      float ch, cl;
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        double* m = side ? mh : ml;
+        float& cm = side ? ch : cl;
+        bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+        const FaceInfo& F = side ? FH : FL;
+        if (inner || F.kind != 3) {
+          int fs = inner ? (side ? l : l - stride) : CPB + side * MAXL1 + (ND == 3 ? ii[T2(d)] : 0) * BS + ii[T1(d)];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) m[v] = sF[v * NG + fs];
+          cm = sC[fs];
+        } else {
+          constexpr int CNT = ND == 3 ? 4 : 2;
+          const float w = 1.0f / (float)CNT;
+          int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
+#pragma unroll
+          for (int qq = 0; qq < CNT; ++qq) {
+            int fs = CPB + side * MAXL1 + (ND == 3 ? (2 * a2 + (qq >> 1)) * F.n1 : 0) + 2 * a1 + (qq & 1);
+            if (flux_kind == 0) {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) m[v] = qq == 0 ? sF[v * NG + fs] * (double)w : m[v] + sF[v * NG + fs] * (double)w;
+            } else {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+                float t = (float)sF[v * NG + fs] * w;
+                m[v] = qq == 0 ? (double)t : (double)((float)m[v] + t);
+              }
+            }
+            cm = qq == 0 ? sC[fs] * w : cm + sC[fs] * w;
+          }
+        }
+      }
+      if (flux_kind == 0) {  // Float64 differences rounded into the Float32 residual once per dimension (R .-= ...)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) res[q][v] = (float)((double)res[q][v] - (mh[v] - ml[v]) / (double)hd);
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) res[q][v] = res[q][v] - ((float)mh[v] - (float)ml[v]) / hd;
+      }
+      cf[q] = cf[q] + (ch + cl) / hd;
+    }
+    __syncthreads();
+    stride *= BS;
+  }
+#pragma unroll
+  for (int q = 0; q < C::CPT; ++q) {
+    int l = tid + q * NT;
+    if (l >= CPB) break;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) R[(int64_t)v * N + cell0 + l] = res[q][v];
+    cfl[cell0 + l] = cf[q];
+  }
+}
+
+// Q -> P, elementwise (src/cfd.jl:137-151)
+template <int ND>
+__global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float q[ND + 2], p[ND + 2];
+#pragma unroll
+    for (int v = 0; v < ND + 2; ++v) q[v] = Q[(int64_t)v * n + i];
+    s2p<ND>(f, q, p);
+#pragma unroll
+    for (int v = 0; v < ND + 2; ++v) P[(int64_t)v * n + i] = p[v];
+  }
+}
+
+template <int ND, int BS, bool FINER>
+int launch_pair(ibx_ctx* c, const ibx_domain& D, const int32_t* sens_blocks, int n_sens, const int32_t* flux_blocks,
+                int n_flux, ibx_fluid f, int flux_kind, const float* P, float* S, float* R, float* cfl, int stage) {
+  using C = Cfg<ND, BS, FINER>;
+  if (stage == 0) {
+    if (n_sens == 0) return IBX_OK;
+    static bool attr = false;
+    if (!attr && C::SMEM_SENSOR > 48 * 1024) {
+      CU(cudaFuncSetAttribute(k_tile_sensor<ND, BS, FINER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_SENSOR));
+      attr = true;
+    }
+    k_tile_sensor<ND, BS, FINER><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
+    LAUNCH_CHECK();
+  } else {
+    if (n_flux == 0) return IBX_OK;
+    static bool attr = false;
+    if (!attr) {
+      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FLUX));
+      attr = true;
+    }
+    k_tile_flux<ND, BS, FINER><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f,
+                                                                            flux_kind, P, S, R, cfl);
+    LAUNCH_CHECK();
+  }
+  return IBX_OK;
+}
+
+template <int ND, int BS>
+int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S, float* R, float* cfl) {
+  int64_t N = D.ncells;
+  k_prim<ND><<<grid_for(N, 256, c->sm_count, 16), 256, 0, c->stream>>>(f, Q, P, N);
+  LAUNCH_CHECK();
+  int rc;
+  // sensor on every local block (owned + halo blocks of a shard), fluxes on the owned blocks only
+  if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+  if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+  if ((rc = launch_pair<ND, BS, false>(c, D, nullptr, 0, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl, 1))) return rc;
+  if ((rc = launch_pair<ND, BS, true>(c, D, nullptr, 0, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl, 1))) return rc;
+  return IBX_OK;
+}
+
+}  // namespace
+
+namespace ibx {
+
+bool tile_supported(const ibx_domain& D) { return D.block_size == 8 || D.block_size == 4 || D.block_size == 2; }
+
+// Euler residual through the tile kernels; P (N x nv) and S (N) are scratch
+int residual_euler_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,
+                         float* R, float* cfl) {
+  if (D.nd == 3) {
+    if (D.block_size == 8) return run_tiles<3, 8>(c, D, f, flux_kind, Q, P, S, R, cfl);
+    if (D.block_size == 4) return run_tiles<3, 4>(c, D, f, flux_kind, Q, P, S, R, cfl);
+    return run_tiles<3, 2>(c, D, f, flux_kind, Q, P, S, R, cfl);
+  }
+  if (D.block_size == 8) return run_tiles<2, 8>(c, D, f, flux_kind, Q, P, S, R, cfl);
+  if (D.block_size == 4) return run_tiles<2, 4>(c, D, f, flux_kind, Q, P, S, R, cfl);
+  return run_tiles<2, 2>(c, D, f, flux_kind, Q, P, S, R, cfl);
+}
+
+}  // namespace ibx

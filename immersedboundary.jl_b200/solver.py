@@ -96,7 +96,8 @@ def hutchinson_trick(f, X, n_samples, h=1e-6, fX=None, rng=None):
             acc += J * dz
         acc = acc / float(n_samples)
         for j in range(nv):
-            call("ibx_array_set_column", context(), D.h, j + nv * i, acc.col(j).h)
+            colj = acc.col(j)  # keep the temporary alive across the call
+            call("ibx_array_set_column", context(), D.h, j + nv * i, colj.h)
     return D
 
 
