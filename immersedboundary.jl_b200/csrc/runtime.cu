@@ -39,7 +39,7 @@ static void free_tables(ibx_domain& D) {
     for (auto& B : F.parts) { fr(B.d_ghost); fr(B.d_ptr); fr(B.d_idx_global); fr(B.d_image_domain); fr(B.d_idx); fr(B.d_w); fr(B.d_normals); fr(B.d_eta); }
   for (auto& S : D.surfaces) fr(S.d_areas);
   fr(D.d_block_faces); fr(D.d_block_h);
-  fr(D.d_blk_all_plain); fr(D.d_blk_all_finer); fr(D.d_blk_own_plain); fr(D.d_blk_own_finer);
+  fr(D.d_blk_all_plain); fr(D.d_blk_all_finer); fr(D.d_blk_own_plain); fr(D.d_blk_own_finer); fr(D.d_blk_own_regular);
   for (auto& p : D.shard.d_send) fr(p);
   for (auto& p : D.shard.d_recv) fr(p);
   for (auto& p : D.shard.d_sendbuf) fr(p);
@@ -308,12 +308,27 @@ int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
     int64_t cpb = 1;
     for (int k = 0; k < nd; ++k) cpb *= D.block_size;
     int64_t nblk = D.ncells / cpb, nown = D.shard.active ? D.shard.n_owned / cpb : nblk;
-    std::vector<int32_t> ap, af, op, of;
+    std::vector<int32_t> ap, af, op, of, oreg;
     for (int64_t b = 0; b < nblk; ++b) {
-      bool finer = false;
-      for (int f = 0; f < 2 * nd; ++f) finer |= D.block_faces[(size_t)b * 2 * nd + f].kind == 3;
+      bool finer = false, regular = true;
+      for (int f = 0; f < 2 * nd; ++f) {
+        finer |= D.block_faces[(size_t)b * 2 * nd + f].kind == 3;
+        regular &= D.block_faces[(size_t)b * 2 * nd + f].kind == 1;
+      }
       (finer ? af : ap).push_back((int32_t)b);
-      if (b < nown) (finer ? of : op).push_back((int32_t)b);
+      if (b < nown) {
+        if (regular) oreg.push_back((int32_t)b);
+        else (finer ? of : op).push_back((int32_t)b);
+      }
+    }
+    D.n_own_regular = (int)oreg.size();
+    if ((rc = upload_vec(c, oreg, &D.d_blk_own_regular))) return rc;
+    D.all_pow2 = true;
+    for (float hv : D.block_h) {
+      uint32_t u;
+      memcpy(&u, &hv, 4);
+      uint32_t e = (u >> 23) & 0xffu;
+      if ((u & 0x007fffffu) != 0u || e <= 32u || e >= 222u || (u >> 31)) D.all_pow2 = false;
     }
     D.n_all_plain = (int)ap.size(); D.n_all_finer = (int)af.size(); D.n_own_plain = (int)op.size(); D.n_own_finer = (int)of.size();
     if ((rc = upload_vec(c, ap, &D.d_blk_all_plain))) return rc;

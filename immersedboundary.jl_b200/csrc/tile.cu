@@ -32,8 +32,8 @@ struct Cfg {
   static constexpr int NG = CPB + 2 * MAXL1;                             // gradient / flux slots per dimension
   static constexpr int NT = CPB >= 512 ? 256 : (CPB >= 64 ? 64 : 32);
   static constexpr int CPT = (CPB + NT - 1) / NT;
-  // doubles first (8-byte alignment): face fluxes [NV][NG]; then floats: P [NV][NS], D [NS], gradient [NV][NG], CFL term [NG]
-  static constexpr size_t SMEM_FLUX = sizeof(double) * (size_t)NV * NG + sizeof(float) * ((size_t)(NV + 1) * NS + (size_t)(NV + 1) * NG);
+  // doubles first (8-byte alignment): face fluxes [NV][NG]; then floats: P [NV][NS], D [NS], CFL term [NG]
+  static constexpr size_t SMEM_FLUX = sizeof(double) * (size_t)NV * NG + sizeof(float) * ((size_t)(NV + 1) * NS + (size_t)NG);
   static constexpr size_t SMEM_SENSOR = sizeof(float) * ((size_t)CPB + NFACES * MAXL1);
 };
 
@@ -186,21 +186,102 @@ k_tile_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ flux pass
-template <int ND, int BS, bool FINER>
-__global__ void __launch_bounds__(Cfg<ND, BS, FINER>::NT)
+// Green-Gauss gradient along d of the NV staged variables at OWN cell l (src/ImmersedBoundary.jl:918-926, :965-972)
+template <int ND, int BS, bool FINER, int NV, int NS>
+__device__ __forceinline__ void own_grad(const float* __restrict__ sP, const FaceInfo& FL, const FaceInfo& FH, int l,
+                                         const int (&ii)[3], int d, int stride, float hd, bool p2, float inv_hd, float* g) {
+  float m[2][NV];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+    if (inner) {
+      int n = side ? l + stride : l - stride;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + n], hd, hd, p2);
+    } else {
+      const FaceInfo& F = side ? FH : FL;
+      if (F.kind == 0) {  // box face: owner == neighbour == l
+#pragma unroll
+        for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + l], hd, hd, p2);
+      } else if (!FINER || F.kind != 3) {
+        int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
+        int n = F.base + (F.kind == 1 ? a2 * F.n1 + a1 : (a2 >> 1) * F.n1 + (a1 >> 1));
+        const bool ff = p2 && F.kind == 1;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + n], hd, F.hn, ff);
+      } else {
+        int slot[4];
+        int cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
+        float w = 1.0f / (float)cnt;
+        for (int q = 0; q < cnt; ++q) {
+          int n = F.base + slot[q];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            float fv = face_interp(sP[v * NS + l], sP[v * NS + n], hd, F.hn);
+            m[side][v] = q == 0 ? fv * w : m[side][v] + fv * w;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v] = p2 ? (m[1][v] - m[0][v]) * inv_hd : (m[1][v] - m[0][v]) / hd;
+}
+
+// gradient along d at halo cell r (layer 0) of face (d, side): far side = its layer-1 twin, near side = own cells
+template <int ND, int BS, bool FINER, int NV, int NS>
+__device__ __forceinline__ void halo_grad(const float* __restrict__ sP, const FaceInfo& F, int side, int r, int d, float hd,
+                                          bool p2, float* g) {
+  int j1 = r % F.n1, j2 = r / F.n1;
+  int n = F.base + r, far = n + F.n1 * F.n2;
+  float hc = F.hn;
+  int bnd = side ? BS - 1 : 0;
+  float nearv[NV], farv[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) farv[v] = face_interp_f(sP[v * NS + n], sP[v * NS + far], hc, hc, p2);
+  if (F.kind == 1) {
+    int o = compose<ND, BS>(d, bnd, j1, j2);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) nearv[v] = face_interp_f(sP[v * NS + n], sP[v * NS + o], hc, hd, p2);
+  } else if (FINER && F.kind == 3) {
+    int o = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+  } else {  // coarser halo cell: 2^(ND-1) own fine cells face it, ascending cell id
+    constexpr int CNT = ND == 3 ? 4 : 2;
+    const float w = 1.0f / (float)CNT;
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) {
+      int o = compose<ND, BS>(d, bnd, 2 * j1 + (q & 1), 2 * j2 + (q >> 1));
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float fv = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+        nearv[v] = q == 0 ? fv * w : nearv[v] + fv * w;
+      }
+    }
+  }
+  const float invc = 1.0f / hc;  // exact when p2 (hc = hd, 2 hd or hd / 2)
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float df = side ? farv[v] - nearv[v] : nearv[v] - farv[v];
+    g[v] = p2 ? df * invc : df / hc;
+  }
+}
+
+template <int ND, int BS, bool FINER, int FLUX>
+__global__ void __launch_bounds__(Cfg<ND, BS, FINER>::NT, (ND == 3 && BS == 8 && !FINER) ? 3 : 1)
 k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
-            int64_t N, ibx_fluid fl, int flux_kind, const float* __restrict__ P, const float* __restrict__ Dg,
+            int64_t N, ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg,
             float* __restrict__ R, float* __restrict__ cfl) {
   using C = Cfg<ND, BS, FINER>;
   constexpr int NV = C::NV, CPB = C::CPB, NT = C::NT, NS = C::NS, NG = C::NG, MAXL1 = C::MAXL1;
   extern __shared__ double smem_d[];
   __shared__ FaceInfo fi[C::NFACES];
-  double* sF = smem_d;              // [NV][NG] face fluxes of the current dimension (Float64, see hll_flux)
-  float* sP = (float*)(sF + NV * NG);  // [NV][NS] primitives
-  float* sD = sP + NV * NS;         // [NS]     sensor
-  float* sG = sD + NS;              // [NV][NG] gradient along the current dimension
-  float* sC = sG + NV * NG;         // [NG]     CFL term of each face
   __shared__ float h[3];
+  double* sF = smem_d;                 // [NV][NG] face fluxes of the current dimension (Float64, see hll_flux)
+  float* sP = (float*)(sF + NV * NG);  // [NV][NS] primitives
+  float* sD = sP + NV * NS;            // [NS]     sensor
+  float* sC = sD + NS;                 // [NG]     CFL term of each face
   const int64_t b = blocks[blockIdx.x];
   const int tid = threadIdx.x;
   if (tid < C::NFACES) fill_face_info<ND, BS>(fi[tid], faces[b * C::NFACES + tid], CPB + tid * 2 * MAXL1, bh[b * ND + (tid >> 1)]);
@@ -242,136 +323,79 @@ k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
 #pragma unroll 1
   for (int d = 0; d < ND; ++d) {
     const float hd = h[d];
+    const bool p2 = is_pow2(hd);                 // exact fast paths (see physics.cuh) on same-spacing faces
+    const float inv_hd = 1.0f / hd;              // exact when p2
+    const double inv_hd_d = 1.0 / (double)hd;
     const FaceInfo& FL = fi[2 * d];
     const FaceInfo& FH = fi[2 * d + 1];
-    const int nl = FL.kind ? FL.n1 * FL.n2 : 0, nh = FH.kind ? FH.n1 * FH.n2 : 0;
-    // ---- (1) Green-Gauss gradient along d: own cells, then layer-0 halo cells of the two faces normal to d
-    for (int it = tid; it < CPB + nl + nh; it += NT) {
-      float m[2][NV];
-      float hc;
-      int gslot;
-      if (it < CPB) {
-        const int l = it;
-        int ii[3];
-        split<ND, BS>(l, ii);
-        hc = hd;
-        gslot = l;
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
-          if (inner) {
-            int n = side ? l + stride : l - stride;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) m[side][v] = face_interp(sP[v * NS + l], sP[v * NS + n], hd, hd);
-          } else {
-            const FaceInfo& F = side ? FH : FL;
-            if (F.kind == 0) {
-#pragma unroll
-              for (int v = 0; v < NV; ++v) m[side][v] = face_interp(sP[v * NS + l], sP[v * NS + l], hd, hd);
-            } else {
-              int slot[4];
-              int cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
-              float w = 1.0f / (float)cnt;
-              for (int q = 0; q < cnt; ++q) {
-                int n = F.base + slot[q];
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                  float fv = face_interp(sP[v * NS + l], sP[v * NS + n], hd, F.hn);
-                  m[side][v] = q == 0 ? fv * w : m[side][v] + fv * w;
-                }
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) sG[v * NG + gslot] = (m[1][v] - m[0][v]) / hc;
-      } else {
-        // halo cell n in layer 0 of face (d, side): far side = its layer-1 twin, near side = own cells
-        int side = it - CPB >= nl ? 1 : 0;
-        const FaceInfo& F = side ? FH : FL;
-        int r = it - CPB - (side ? nl : 0);
-        int j1 = r % F.n1, j2 = r / F.n1;
-        int n = F.base + r, far = n + F.n1 * F.n2;
-        hc = F.hn;
-        gslot = CPB + side * MAXL1 + r;
-        int bnd = side ? BS - 1 : 0;
-        float nearv[NV], farv[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) farv[v] = face_interp(sP[v * NS + n], sP[v * NS + far], hc, hc);
-        if (F.kind == 1) {
-          int o = compose<ND, BS>(d, bnd, j1, j2);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
-        } else if (F.kind == 3) {
-          int o = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
-        } else {  // coarser halo cell: 2^(ND-1) own fine cells face it
-          constexpr int CNT = ND == 3 ? 4 : 2;
-          const float w = 1.0f / (float)CNT;
-#pragma unroll
-          for (int q = 0; q < CNT; ++q) {
-            int o = compose<ND, BS>(d, bnd, 2 * j1 + (q & 1), 2 * j2 + (q >> 1));
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              float fv = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
-              nearv[v] = q == 0 ? fv * w : nearv[v] + fv * w;
-            }
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) sG[v * NG + gslot] = side ? (farv[v] - nearv[v]) / hc : (nearv[v] - farv[v]) / hc;
-      }
-    }
-    __syncthreads();
-    // ---- (2) face fluxes along d, each face once: internal faces (slot = owner cell), low face, high face
+    // ---- (1) face fluxes along d, each face once: internal faces (slot = owner cell), low face, high face.
+    //      Cell gradients (Green-Gauss along d) are formed on the fly from the staged primitives.
     const int nfl = FL.nfaces, nfh = FH.nfaces;
     for (int it = tid; it < CPB + nfl + nfh; it += NT) {
-      int so, sn, go, gn, fslot;  // staged-cell slots and gradient slots of owner / neighbour
-      float ho, hn;
+      float po[NV], pn[NV], g0[NV], g1[NV];
+      float ho, hn, Do, Dn;
+      int fslot;
       if (it < CPB) {
         int ii[3];
         split<ND, BS>(it, ii);
         if (ii[d] == BS - 1) continue;
-        so = it; sn = it + stride; go = so; gn = sn; ho = hd; hn = hd; fslot = it;
+        const int so = it, sn = it + stride;
+        own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, so, ii, d, stride, hd, p2, inv_hd, g0);
+        ii[d] += 1;
+        own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, sn, ii, d, stride, hd, p2, inv_hd, g1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + so]; pn[v] = sP[v * NS + sn]; }
+        Do = sD[so]; Dn = sD[sn];
+        ho = hd; hn = hd; fslot = it;
       } else {
-        int side = it - CPB >= nfl ? 1 : 0;
+        const int side = it - CPB >= nfl ? 1 : 0;
         const FaceInfo& F = side ? FH : FL;
-        int k = it - CPB - (side ? nfl : 0);
-        int bnd = side ? BS - 1 : 0;
-        int own, hs, hg;
-        float hh = F.hn;
-        if (F.kind == 3) {
+        const int k = it - CPB - (side ? nfl : 0);
+        const int bnd = side ? BS - 1 : 0;
+        int own, hs = -1, hr = 0;
+        if (FINER && F.kind == 3) {
           int j1 = k % F.n1, j2 = k / F.n1;
           own = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
-          hs = F.base + k;
-          hg = CPB + side * MAXL1 + k;
+          hr = k;
         } else {
           int a1 = k % BS, a2 = k / BS;
           own = compose<ND, BS>(d, bnd, a1, a2);
-          if (F.kind == 0) { hs = own; hg = own; hh = hd; }
-          else {
-            int r = F.kind == 1 ? k : (a2 >> 1) * F.n1 + (a1 >> 1);
-            hs = F.base + r;
-            hg = CPB + side * MAXL1 + r;
-          }
+          hr = F.kind == 1 ? k : (a2 >> 1) * F.n1 + (a1 >> 1);
         }
-        if (side) { so = own; go = own; ho = hd; sn = hs; gn = hg; hn = hh; }
-        else      { so = hs; go = hg; ho = hh; sn = own; gn = own; hn = hd; }
+        int ii[3];
+        split<ND, BS>(own, ii);
+        float gown[NV], ghal[NV], pown[NV], phal[NV];
+        own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, own, ii, d, stride, hd, p2, inv_hd, gown);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) pown[v] = sP[v * NS + own];
+        float Down = sD[own], Dhal, hh;
+        if (F.kind == 0) {  // box face: both sides are the own cell
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { phal[v] = pown[v]; ghal[v] = gown[v]; }
+          Dhal = Down; hh = hd;
+        } else {
+          hs = F.base + hr;
+          halo_grad<ND, BS, FINER, NV, NS>(sP, F, side, hr, d, hd, p2, ghal);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) phal[v] = sP[v * NS + hs];
+          Dhal = sD[hs]; hh = F.hn;
+        }
+        if (side) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { po[v] = pown[v]; g0[v] = gown[v]; pn[v] = phal[v]; g1[v] = ghal[v]; }
+          Do = Down; Dn = Dhal; ho = hd; hn = hh;
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { po[v] = phal[v]; g0[v] = ghal[v]; pn[v] = pown[v]; g1[v] = gown[v]; }
+          Do = Dhal; Dn = Down; ho = hh; hn = hd;
+        }
         fslot = CPB + side * MAXL1 + k;
       }
-      float po[NV], pn[NV], g0[NV], g1[NV], pl[NV], pr[NV];
+      float pl[NV], pr[NV];
       double F_[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        po[v] = sP[v * NS + so];
-        pn[v] = sP[v * NS + sn];
-        g0[v] = sG[v * NG + go];
-        g1[v] = sG[v * NG + gn];
-      }
-      float Do = sD[so], Dn = sD[sn];
-      muscl_face<NV>(po, pn, g0, g1, ho, hn, Do, Dn, true, false, pl, pr);
-      if (flux_kind == 0) {
+      const bool fast = p2 && ho == hn;
+      muscl_face<NV>(po, pn, g0, g1, ho, hn, Do, Dn, true, false, pl, pr, fast);
+      if (FLUX == 0) {
         hll_flux<ND>(fl, pl, pr, d, F_);
       } else {
         float Ff[NV];
@@ -380,13 +404,13 @@ k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
         for (int v = 0; v < NV; ++v) F_[v] = (double)Ff[v];
       }
       float ao = sqrtf(gr * clampT(po[1])), an = sqrtf(gr * clampT(pn[1]));
-      float ct = fabsf(face_interp(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), ho, hn)) + face_interp(ao, an, ho, hn);
+      float ct = fabsf(face_interp_f(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), ho, hn, fast)) + face_interp_f(ao, an, ho, hn, fast);
 #pragma unroll
       for (int v = 0; v < NV; ++v) sF[v * NG + fslot] = F_[v];
       sC[fslot] = ct;
     }
     __syncthreads();
-    // ---- (3) divergence: R -= (mean_high - mean_low) / h, cfl += (c_high + c_low) / h
+    // ---- (2) divergence: R -= (mean_high - mean_low) / h, cfl += (c_high + c_low) / h
 #pragma unroll
     for (int q = 0; q < C::CPT; ++q) {
       int l = tid + q * NT;
@@ -401,7 +425,7 @@ k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
         float& cm = side ? ch : cl;
         bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
         const FaceInfo& F = side ? FH : FL;
-        if (inner || F.kind != 3) {
+        if (inner || !FINER || F.kind != 3) {
           int fs = inner ? (side ? l : l - stride) : CPB + side * MAXL1 + (ND == 3 ? ii[T2(d)] : 0) * BS + ii[T1(d)];
 #pragma unroll
           for (int v = 0; v < NV; ++v) m[v] = sF[v * NG + fs];
@@ -413,7 +437,7 @@ k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
 #pragma unroll
           for (int qq = 0; qq < CNT; ++qq) {
             int fs = CPB + side * MAXL1 + (ND == 3 ? (2 * a2 + (qq >> 1)) * F.n1 : 0) + 2 * a1 + (qq & 1);
-            if (flux_kind == 0) {
+            if (FLUX == 0) {
 #pragma unroll
               for (int v = 0; v < NV; ++v) m[v] = qq == 0 ? sF[v * NG + fs] * (double)w : m[v] + sF[v * NG + fs] * (double)w;
             } else {
@@ -427,14 +451,14 @@ k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
           }
         }
       }
-      if (flux_kind == 0) {  // Float64 differences rounded into the Float32 residual once per dimension (R .-= ...)
+      if (FLUX == 0) {  // Float64 differences rounded into the Float32 residual once per dimension (R .-= ...)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) res[q][v] = (float)((double)res[q][v] - (mh[v] - ml[v]) / (double)hd);
+        for (int v = 0; v < NV; ++v) res[q][v] = (float)((double)res[q][v] - (mh[v] - ml[v]) * inv_hd_d);
       } else {
 #pragma unroll
         for (int v = 0; v < NV; ++v) res[q][v] = res[q][v] - ((float)mh[v] - (float)ml[v]) / hd;
       }
-      cf[q] = cf[q] + (ch + cl) / hd;
+      cf[q] = cf[q] + (p2 ? (ch + cl) * inv_hd : (ch + cl) / hd);
     }
     __syncthreads();
     stride *= BS;
@@ -447,6 +471,169 @@ k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
     for (int v = 0; v < NV; ++v) R[(int64_t)v * N + cell0 + l] = res[q][v];
     cfl[cell0 + l] = cf[q];
   }
+}
+
+// ------------------------------------------------------------------------------------------ regular blocks
+// Lean flux kernel for blocks whose 2*ND neighbours are all same-level blocks (80 % of the C4 mesh): the staged tile
+// is a plain (BS+4)^ND padded array, every face of a dimension is one item of one uniform loop, no per-face
+// descriptors, no branches.  Same arithmetic, same order, same bits as k_tile_flux; compact enough for the 32 KB
+// instruction cache, which the general kernel is not.
+template <int ND, int BS>
+struct RegCfg {
+  static constexpr int NV = ND + 2;
+  static constexpr int PAD = BS + 4;
+  static constexpr int TS = ND == 3 ? PAD * PAD * PAD : PAD * PAD;           // padded tile slots
+  static constexpr int CPB = ND == 3 ? BS * BS * BS : BS * BS;
+  static constexpr int FACE = ND == 3 ? BS * BS : BS;
+  static constexpr int NFD = (BS + 1) * FACE;                                // faces per dimension
+  static constexpr int NT = (ND == 3 && BS == 8) ? 192 : (CPB >= 64 ? 64 : 32);
+  static constexpr int CPT = (CPB + NT - 1) / NT;
+  static constexpr size_t SMEM = sizeof(double) * (size_t)NV * NFD + sizeof(float) * ((size_t)(NV + 1) * TS + NFD);
+};
+
+template <int ND, int BS, bool P2, int FLUX>
+__global__ void __launch_bounds__(RegCfg<ND, BS>::NT, (ND == 3 && BS == 8) ? 3 : 1)
+k_reg_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
+           ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, float* __restrict__ R,
+           float* __restrict__ cfl) {
+  using C = RegCfg<ND, BS>;
+  constexpr int NV = C::NV, PAD = C::PAD, TS = C::TS, CPB = C::CPB, NT = C::NT, NFD = C::NFD, FACE = C::FACE;
+  extern __shared__ double smem_d[];
+  double* sF = smem_d;                  // [NV][NFD] fluxes of the current dimension
+  float* sP = (float*)(sF + NV * NFD);  // [NV][TS]
+  float* sD = sP + NV * TS;             // [TS]
+  float* sC = sD + TS;                  // [NFD]
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int64_t cell0 = b * CPB;
+  // ---- stage: own cells, then two layers of each same-level neighbour
+  for (int l = tid; l < CPB; l += NT) {
+    int ii[3];
+    split<ND, BS>(l, ii);
+    int s = (ii[0] + 2) + PAD * ((ii[1] + 2) + (ND == 3 ? PAD * (ii[2] + 2) : 0));
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sP[v * TS + s] = P[(int64_t)v * N + cell0 + l];
+    sD[s] = Dg[cell0 + l];
+  }
+  for (int k = tid; k < 2 * ND * 2 * FACE; k += NT) {
+    int f = k / (2 * FACE), r = k - f * 2 * FACE;
+    int layer = r / FACE, q = r - layer * FACE;
+    int d = f >> 1, side = f & 1;
+    int j1 = q % BS, j2 = q / BS;
+    int64_t nb = faces[b * (2 * ND) + f].nb[0];
+    int64_t c = nb * CPB + compose<ND, BS>(d, side ? layer : BS - 1 - layer, j1, j2);
+    int cc[3] = {0, 0, 0};
+    cc[d] = side ? BS + layer : -1 - layer;
+    cc[T1(d)] = j1;
+    if (ND == 3) cc[T2(d)] = j2;
+    int s = (cc[0] + 2) + PAD * ((cc[1] + 2) + (ND == 3 ? PAD * (cc[2] + 2) : 0));
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sP[v * TS + s] = P[(int64_t)v * N + c];
+    sD[s] = Dg[c];
+  }
+  __syncthreads();
+  float res[C::CPT][NV], cf[C::CPT];
+#pragma unroll
+  for (int q = 0; q < C::CPT; ++q) {
+    cf[q] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) res[q][v] = 0.0f;
+  }
+  const float gr = fl.gamma * fl.R;
+#pragma unroll 1   // keep the body once: the loop must stay inside the 32 KB instruction cache
+  for (int d = 0; d < ND; ++d) {
+    const float hd = bh[b * ND + d];
+    const float inv_hd = 1.0f / hd;
+    const double inv_hd_d = 1.0 / (double)hd;
+    constexpr int n0 = BS, n1 = BS;
+    const int m0 = d == 0 ? BS + 1 : BS, m1 = d == 1 ? BS + 1 : BS;   // extents of the face index space
+    const int ss = d == 0 ? 1 : (d == 1 ? PAD : PAD * PAD);           // tile stride along d
+    (void)n0; (void)n1;
+    // ---- (1) every face normal to d once: owner o = cell (c_d - 1), neighbour n = cell c_d
+    for (int it = tid; it < NFD; it += NT) {
+      int c0 = it % m0, c1 = (it / m0) % m1, c2 = ND == 3 ? it / (m0 * m1) : 0;
+      int so = (c0 + 2) + PAD * ((c1 + 2) + (ND == 3 ? PAD * (c2 + 2) : 0)) - ss;  // owner sits one step below along d
+      int sn = so + ss;
+      float po[NV], pn[NV], g0[NV], g1[NV], pl[NV], pr[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float um = sP[v * TS + so - ss], uo = sP[v * TS + so], un = sP[v * TS + sn], up = sP[v * TS + sn + ss];
+        float fm = face_interp_f(um, uo, hd, hd, P2), fc = face_interp_f(uo, un, hd, hd, P2), fp = face_interp_f(un, up, hd, hd, P2);
+        g0[v] = P2 ? (fc - fm) * inv_hd : (fc - fm) / hd;
+        g1[v] = P2 ? (fp - fc) * inv_hd : (fp - fc) / hd;
+        po[v] = uo;
+        pn[v] = un;
+      }
+      float Do = sD[so], Dn = sD[sn];
+      muscl_face<NV>(po, pn, g0, g1, hd, hd, Do, Dn, true, false, pl, pr, P2);
+      double F_[NV];
+      if (FLUX == 0) {
+        hll_flux<ND>(fl, pl, pr, d, F_);
+      } else {
+        float Ff[NV];
+        rusanov_flux<ND>(fl, pl, pr, face_interp(Do, Dn, hd, hd), d, Ff);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) F_[v] = (double)Ff[v];
+      }
+      float ao = sqrtf(gr * clampT(po[1])), an = sqrtf(gr * clampT(pn[1]));
+      float ct = fabsf(face_interp_f(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), hd, hd, P2)) + face_interp_f(ao, an, hd, hd, P2);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sF[v * NFD + it] = F_[v];
+      sC[it] = ct;
+    }
+    __syncthreads();
+    // ---- (2) divergence
+#pragma unroll
+    for (int q = 0; q < C::CPT; ++q) {
+      int l = tid + q * NT;
+      if (l < CPB) {
+        int ii[3];
+        split<ND, BS>(l, ii);
+        int lo = ii[0] + m0 * (ii[1] + (ND == 3 ? m1 * ii[2] : 0));      // low face: c_d = i_d
+        int hi = lo + (d == 0 ? 1 : (d == 1 ? m0 : m0 * m1));            // high face: c_d = i_d + 1
+        if (FLUX == 0) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            res[q][v] = (float)((double)res[q][v] - (sF[v * NFD + hi] - sF[v * NFD + lo]) * inv_hd_d);
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) res[q][v] = res[q][v] - ((float)sF[v * NFD + hi] - (float)sF[v * NFD + lo]) / hd;
+        }
+        float cs = sC[hi] + sC[lo];
+        cf[q] = cf[q] + (P2 ? cs * inv_hd : cs / hd);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < C::CPT; ++q) {
+    int l = tid + q * NT;
+    if (l < CPB) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) R[(int64_t)v * N + cell0 + l] = res[q][v];
+      cfl[cell0 + l] = cf[q];
+    }
+  }
+}
+
+template <int ND, int BS, bool P2>
+int launch_reg(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* P, const float* S, float* R, float* cfl) {
+  using C = RegCfg<ND, BS>;
+  if (D.n_own_regular == 0) return IBX_OK;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  if (flux_kind == 0)
+    k_reg_flux<ND, BS, P2, 0><<<D.n_own_regular, C::NT, C::SMEM, c->stream>>>(D.d_blk_own_regular, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
+  else
+    k_reg_flux<ND, BS, P2, 1><<<D.n_own_regular, C::NT, C::SMEM, c->stream>>>(D.d_blk_own_regular, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
+  LAUNCH_CHECK();
+  return IBX_OK;
 }
 
 // Q -> P, elementwise (src/cfd.jl:137-151)
@@ -479,11 +666,16 @@ int launch_pair(ibx_ctx* c, const ibx_domain& D, const int32_t* sens_blocks, int
     if (n_flux == 0) return IBX_OK;
     static bool attr = false;
     if (!attr) {
-      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FLUX));
+      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FLUX));
+      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FLUX));
+      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       attr = true;
     }
-    k_tile_flux<ND, BS, FINER><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f,
-                                                                            flux_kind, P, S, R, cfl);
+    if (flux_kind == 0)
+      k_tile_flux<ND, BS, FINER, 0><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
+    else
+      k_tile_flux<ND, BS, FINER, 1><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
     LAUNCH_CHECK();
   }
   return IBX_OK;
@@ -498,6 +690,8 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   // sensor on every local block (owned + halo blocks of a shard), fluxes on the owned blocks only
   if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
   if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+  // fluxes: regular blocks (all neighbours same level) through the lean kernel, the rest through the general one
+  if ((rc = D.all_pow2 ? launch_reg<ND, BS, true>(c, D, f, flux_kind, P, S, R, cfl) : launch_reg<ND, BS, false>(c, D, f, flux_kind, P, S, R, cfl))) return rc;
   if ((rc = launch_pair<ND, BS, false>(c, D, nullptr, 0, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl, 1))) return rc;
   if ((rc = launch_pair<ND, BS, true>(c, D, nullptr, 0, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl, 1))) return rc;
   return IBX_OK;
