@@ -200,8 +200,8 @@ struct ibx_domain {
   float* d_block_h = nullptr;
   // block work lists of the tile kernels: blocks without / with a finer neighbour; all local vs owned only
   int32_t *d_blk_all_plain = nullptr, *d_blk_all_finer = nullptr, *d_blk_own_plain = nullptr, *d_blk_own_finer = nullptr;
-  int32_t* d_blk_own_regular = nullptr;  // owned blocks whose 2*nd neighbours are all same-level blocks (lean kernel)
-  int n_all_plain = 0, n_all_finer = 0, n_own_plain = 0, n_own_finer = 0, n_own_regular = 0;
+  int32_t *d_blk_own_regular = nullptr, *d_blk_all_regular = nullptr;  // blocks whose 2*nd neighbours are all same-level blocks (lean kernels)
+  int n_all_plain = 0, n_all_finer = 0, n_own_plain = 0, n_own_finer = 0, n_own_regular = 0, n_all_regular = 0;
   bool all_pow2 = false;                 // every cell width is a power of two (exact fast paths, physics.cuh)
   ibx::Shard shard;
   ~ibx_domain();

@@ -39,7 +39,7 @@ static void free_tables(ibx_domain& D) {
     for (auto& B : F.parts) { fr(B.d_ghost); fr(B.d_ptr); fr(B.d_idx_global); fr(B.d_image_domain); fr(B.d_idx); fr(B.d_w); fr(B.d_normals); fr(B.d_eta); }
   for (auto& S : D.surfaces) fr(S.d_areas);
   fr(D.d_block_faces); fr(D.d_block_h);
-  fr(D.d_blk_all_plain); fr(D.d_blk_all_finer); fr(D.d_blk_own_plain); fr(D.d_blk_own_finer); fr(D.d_blk_own_regular);
+  fr(D.d_blk_all_plain); fr(D.d_blk_all_finer); fr(D.d_blk_own_plain); fr(D.d_blk_own_finer); fr(D.d_blk_own_regular); fr(D.d_blk_all_regular);
   for (auto& p : D.shard.d_send) fr(p);
   for (auto& p : D.shard.d_recv) fr(p);
   for (auto& p : D.shard.d_sendbuf) fr(p);
@@ -308,21 +308,24 @@ int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
     int64_t cpb = 1;
     for (int k = 0; k < nd; ++k) cpb *= D.block_size;
     int64_t nblk = D.ncells / cpb, nown = D.shard.active ? D.shard.n_owned / cpb : nblk;
-    std::vector<int32_t> ap, af, op, of, oreg;
+    std::vector<int32_t> ap, af, op, of, oreg, areg;
     for (int64_t b = 0; b < nblk; ++b) {
       bool finer = false, regular = true;
       for (int f = 0; f < 2 * nd; ++f) {
         finer |= D.block_faces[(size_t)b * 2 * nd + f].kind == 3;
         regular &= D.block_faces[(size_t)b * 2 * nd + f].kind == 1;
       }
-      (finer ? af : ap).push_back((int32_t)b);
+      if (regular) areg.push_back((int32_t)b);
+      else (finer ? af : ap).push_back((int32_t)b);
       if (b < nown) {
         if (regular) oreg.push_back((int32_t)b);
         else (finer ? of : op).push_back((int32_t)b);
       }
     }
     D.n_own_regular = (int)oreg.size();
+    D.n_all_regular = (int)areg.size();
     if ((rc = upload_vec(c, oreg, &D.d_blk_own_regular))) return rc;
+    if ((rc = upload_vec(c, areg, &D.d_blk_all_regular))) return rc;
     D.all_pow2 = true;
     for (float hv : D.block_h) {
       uint32_t u;

@@ -636,6 +636,56 @@ int launch_reg(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, cons
   return IBX_OK;
 }
 
+// lean sensor kernel for regular blocks: padded (BS+2)^ND tile of p, uniform loop (same bits as k_tile_sensor)
+template <int ND, int BS, bool P2>
+__global__ void __launch_bounds__(RegCfg<ND, BS>::NT)
+k_reg_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
+             const float* __restrict__ p, float* __restrict__ D) {
+  using C = RegCfg<ND, BS>;
+  constexpr int PAD = BS + 2, CPB = C::CPB, NT = C::NT, FACE = C::FACE;
+  constexpr int TS = ND == 3 ? PAD * PAD * PAD : PAD * PAD;
+  __shared__ float sp[TS];
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int64_t cell0 = b * CPB;
+  for (int l = tid; l < CPB; l += NT) {
+    int ii[3];
+    split<ND, BS>(l, ii);
+    sp[(ii[0] + 1) + PAD * ((ii[1] + 1) + (ND == 3 ? PAD * (ii[2] + 1) : 0))] = p[cell0 + l];
+  }
+  for (int k = tid; k < 2 * ND * FACE; k += NT) {
+    int f = k / FACE, q = k - f * FACE;
+    int d = f >> 1, side = f & 1;
+    int j1 = q % BS, j2 = q / BS;
+    int64_t nb = faces[b * (2 * ND) + f].nb[0];
+    int cc[3] = {0, 0, 0};
+    cc[d] = side ? BS : -1;
+    cc[T1(d)] = j1;
+    if (ND == 3) cc[T2(d)] = j2;
+    sp[(cc[0] + 1) + PAD * ((cc[1] + 1) + (ND == 3 ? PAD * (cc[2] + 1) : 0))] = p[nb * CPB + compose<ND, BS>(d, side ? 0 : BS - 1, j1, j2)];
+  }
+  __syncthreads();
+  float h[ND], ih[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) { h[d] = bh[b * ND + d]; ih[d] = 1.0f / h[d]; }
+  for (int l = tid; l < CPB; l += NT) {
+    int ii[3];
+    split<ND, BS>(l, ii);
+    int s = (ii[0] + 1) + PAD * ((ii[1] + 1) + (ND == 3 ? PAD * (ii[2] + 1) : 0));
+    float pc = sp[s], nu = 1e-7f;
+    int ss = 1;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float fh = sp[s + ss] - pc, fl = pc - sp[s - ss];
+      float gg = P2 ? (fh - fl) * ih[d] : (fh - fl) / h[d];
+      float ug = P2 ? (fabsf(fh) + fabsf(fl)) * ih[d] : (fabsf(fh) + fabsf(fl)) / h[d];
+      nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ug));
+      ss *= PAD;
+    }
+    D[cell0 + l] = nu;
+  }
+}
+
 // Q -> P, elementwise (src/cfd.jl:137-151)
 template <int ND>
 __global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n) {
@@ -688,6 +738,12 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   LAUNCH_CHECK();
   int rc;
   // sensor on every local block (owned + halo blocks of a shard), fluxes on the owned blocks only
+  if (D.n_all_regular) {
+    using RC = RegCfg<ND, BS>;
+    if (D.all_pow2) k_reg_sensor<ND, BS, true><<<D.n_all_regular, RC::NT, 0, c->stream>>>(D.d_blk_all_regular, D.d_block_faces, D.d_block_h, P, S);
+    else k_reg_sensor<ND, BS, false><<<D.n_all_regular, RC::NT, 0, c->stream>>>(D.d_blk_all_regular, D.d_block_faces, D.d_block_h, P, S);
+    LAUNCH_CHECK();
+  }
   if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
   if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
   // fluxes: regular blocks (all neighbours same level) through the lean kernel, the rest through the general one
