@@ -45,7 +45,8 @@ _SCALARS = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "float":
 def _ctype(decl):
     """Map one C parameter declaration to a ctypes type."""
     decl = re.sub(r"/\*.*?\*/", "", decl).strip()
-    decl = re.sub(r"\[\s*\d*\s*\]$", "*", decl)  # `char id[128]` -> pointer
+    if re.search(r"\[\s*\d*\s*\]$", decl):
+        return C.c_void_p  # `char id[128]`: a raw buffer, not a NUL-terminated string
     stars = decl.count("*")
     words = [w for w in re.sub(r"[*]", " ", decl).split() if w != "const"]
     base = words[0]

@@ -133,6 +133,24 @@ int ibx_domain_shard(const ibx_domain* gh, int rank, int nranks, ibx_domain** ou
   // --- local block list: owned blocks, then halo blocks by ascending global id
   std::set<int64_t> halo_blocks;
   for (int64_t c : need) halo_blocks.insert(c / cpb);
+  // A halo block's face towards FINER blocks names 2^(nd-1) blocks, of which only those holding skirt cells are in
+  // the set so far.  The sensor of a skirt cell next to such a face reads one 2^(nd-1) group, which lies in a single
+  // (present) fine block; the siblings are added as placeholders so that the face entry stays addressable.
+  {
+    std::set<int64_t> extra;
+    for (int64_t hb : halo_blocks)
+      for (int f = 0; f < 2 * nd; ++f) {
+        const BlockFace& bf = G.block_faces[(size_t)hb * 2 * nd + f];
+        if (bf.kind != 3) continue;
+        int cnt = nd == 3 ? 4 : 2;
+        bool any = false;
+        for (int q = 0; q < cnt; ++q) any |= (bf.nb[q] >= b0 && bf.nb[q] < b1) || halo_blocks.count(bf.nb[q]);
+        if (any)
+          for (int q = 0; q < cnt; ++q)
+            if (!(bf.nb[q] >= b0 && bf.nb[q] < b1)) extra.insert(bf.nb[q]);
+      }
+    halo_blocks.insert(extra.begin(), extra.end());
+  }
   std::vector<int64_t> lblocks;
   for (int64_t b = b0; b < b1; ++b) lblocks.push_back(b);
   for (int64_t b : halo_blocks) lblocks.push_back(b);
