@@ -636,6 +636,412 @@ int launch_reg(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, cons
   return IBX_OK;
 }
 
+// ------------------------------------------------------------------------------------------ irregular blocks
+// Hybrid flux kernel for blocks with at least one face that is not a same-level contact (domain box, coarser or finer
+// neighbour).  Same padded tile and the same uniform face loop as k_reg_flux; only the faces whose 4-cell stencil
+// touches an irregular block face (the block face itself and the first internal face behind it) take the general
+// path, which reads the coarser / finer halo cells from a separate staging area at their own resolution.
+template <int ND, int BS, bool FINER>
+struct HybCfg {
+  using R = RegCfg<ND, BS>;
+  static constexpr int NV = ND + 2;
+  static constexpr int FACE = R::FACE;
+  static constexpr int MAXL = FINER ? FACE * (ND == 3 ? 4 : 2) : (FACE / (ND == 3 ? 4 : 2) > 0 ? FACE / (ND == 3 ? 4 : 2) : 1);  // cells per irregular halo layer
+  static constexpr int NI = 2 * ND * 2 * MAXL;                 // irregular halo cells (2 layers per face)
+  static constexpr int NX = FINER ? 2 * FACE * (ND == 3 ? 4 : 2) : 0;  // extra flux slots: fine faces of the two block faces of a dimension
+  static constexpr int NSLOT = R::TS + NI;                     // staged cells: padded tile, then irregular halos
+  static constexpr int NFS = R::NFD + NX;
+  static constexpr int NT = R::NT;
+  static constexpr size_t SMEM = sizeof(double) * (size_t)NV * NFS + sizeof(float) * ((size_t)(NV + 1) * NSLOT + NFS);
+};
+
+template <int ND, int BS>
+__device__ __forceinline__ int pslot(const int (&ii)[3]) {
+  constexpr int PAD = BS + 4;
+  return (ii[0] + 2) + PAD * ((ii[1] + 2) + (ND == 3 ? PAD * (ii[2] + 2) : 0));
+}
+template <int ND, int BS>
+__device__ __forceinline__ int pslot_c(int d, int cn, int c1, int c2) {
+  int ii[3] = {0, 0, 0};
+  ii[d] = cn;
+  ii[T1(d)] = c1;
+  if (ND == 3) ii[T2(d)] = c2;
+  return pslot<ND, BS>(ii);
+}
+
+// gradient along d at own cell ii (general: any kind of block face on either side)
+template <int ND, int BS, bool FINER, int NV, int NS>
+__device__ __forceinline__ void hyb_own_grad(const float* __restrict__ sP, const FaceInfo& FL, const FaceInfo& FH, const int (&ii)[3],
+                                             int d, int ss, float hd, bool p2, float inv_hd, float* g) {
+  const int l = pslot<ND, BS>(ii);
+  float m[2][NV];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const FaceInfo& F = side ? FH : FL;
+    bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+    if (inner || F.kind == 1) {   // same-level neighbour: own cell or padded halo slab
+      int n = side ? l + ss : l - ss;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + n], hd, hd, p2);
+    } else if (F.kind == 0) {      // box face: owner == neighbour == this cell
+#pragma unroll
+      for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + l], hd, hd, p2);
+    } else if (!FINER || F.kind == 2) {
+      int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
+      int n = F.base + (a2 >> 1) * F.n1 + (a1 >> 1);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) m[side][v] = face_interp(sP[v * NS + l], sP[v * NS + n], hd, F.hn);
+    } else {
+      int slot[4];
+      int cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
+      float w = 1.0f / (float)cnt;
+      for (int q = 0; q < cnt; ++q) {
+        int n = F.base + slot[q];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float fv = face_interp(sP[v * NS + l], sP[v * NS + n], hd, F.hn);
+          m[side][v] = q == 0 ? fv * w : m[side][v] + fv * w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v] = p2 ? (m[1][v] - m[0][v]) * inv_hd : (m[1][v] - m[0][v]) / hd;
+}
+
+// gradient along d at coarser / finer halo cell r (layer 0) of face (d, side)
+template <int ND, int BS, bool FINER, int NV, int NS>
+__device__ __forceinline__ void hyb_halo_grad(const float* __restrict__ sP, const FaceInfo& F, int side, int r, int d, float hd,
+                                              bool p2, float* g) {
+  int j1 = r % F.n1, j2 = r / F.n1;
+  int n = F.base + r, far = n + F.n1 * F.n2;
+  float hc = F.hn;
+  int bnd = side ? BS - 1 : 0;
+  float nearv[NV], farv[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) farv[v] = face_interp_f(sP[v * NS + n], sP[v * NS + far], hc, hc, p2);
+  if (FINER && F.kind == 3) {
+    int o = pslot_c<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+  } else {
+    constexpr int CNT = ND == 3 ? 4 : 2;
+    const float w = 1.0f / (float)CNT;
+#pragma unroll
+    for (int q = 0; q < CNT; ++q) {
+      int o = pslot_c<ND, BS>(d, bnd, 2 * j1 + (q & 1), 2 * j2 + (q >> 1));
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float fv = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
+        nearv[v] = q == 0 ? fv * w : nearv[v] + fv * w;
+      }
+    }
+  }
+  const float invc = 1.0f / hc;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    float df = side ? farv[v] - nearv[v] : nearv[v] - farv[v];
+    g[v] = p2 ? df * invc : df / hc;
+  }
+}
+
+template <int ND, int BS, bool FINER, bool P2, int FLUX>
+__global__ void __launch_bounds__(HybCfg<ND, BS, FINER>::NT, (ND == 3 && BS == 8 && !FINER) ? 3 : 1)
+k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
+           ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, float* __restrict__ R,
+           float* __restrict__ cfl) {
+  using C = HybCfg<ND, BS, FINER>;
+  using RC = RegCfg<ND, BS>;
+  constexpr int NV = C::NV, PAD = RC::PAD, TS = RC::TS, CPB = RC::CPB, NT = C::NT, NFD = RC::NFD, FACE = RC::FACE;
+  constexpr int NS = C::NSLOT, NFS = C::NFS, MAXL = C::MAXL;
+  extern __shared__ double smem_d[];
+  __shared__ FaceInfo fi[2 * ND];
+  double* sF = smem_d;                  // [NV][NFS]
+  float* sP = (float*)(sF + NV * NFS);  // [NV][NS]
+  float* sD = sP + NV * NS;             // [NS]
+  float* sC = sD + NS;                  // [NFS]
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int64_t cell0 = b * CPB;
+  if (tid < 2 * ND) fill_face_info<ND, BS>(fi[tid], faces[b * (2 * ND) + tid], TS + tid * 2 * MAXL, bh[b * ND + (tid >> 1)]);
+  __syncthreads();
+  // ---- stage own cells into the padded tile
+  for (int l = tid; l < CPB; l += NT) {
+    int ii[3];
+    split<ND, BS>(l, ii);
+    int s = pslot<ND, BS>(ii);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) sP[v * NS + s] = P[(int64_t)v * N + cell0 + l];
+    sD[s] = Dg[cell0 + l];
+  }
+  // ---- halos: same-level faces into the padded slabs, coarser / finer faces into their own areas
+#pragma unroll 1
+  for (int f = 0; f < 2 * ND; ++f) {
+    const FaceInfo& F = fi[f];
+    if (F.kind == 0) continue;
+    int d = f >> 1, side = f & 1, n1n2 = F.n1 * F.n2;
+    for (int k = tid; k < 2 * n1n2; k += NT) {
+      int layer = k / n1n2, r = k - layer * n1n2;
+      int j1 = r % F.n1, j2 = r / F.n1;
+      int64_t c = halo_cell<ND, BS>(F, d, side, j1, j2, layer, CPB);
+      int s = F.kind == 1 ? pslot_c<ND, BS>(d, side ? BS + layer : -1 - layer, j1, j2) : F.base + k;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sP[v * NS + s] = P[(int64_t)v * N + c];
+      sD[s] = Dg[c];
+    }
+  }
+  __syncthreads();
+  float res[RC::CPT][NV], cf[RC::CPT];
+#pragma unroll
+  for (int q = 0; q < RC::CPT; ++q) {
+    cf[q] = 0.0f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) res[q][v] = 0.0f;
+  }
+  const float gr = fl.gamma * fl.R;
+#pragma unroll 1
+  for (int d = 0; d < ND; ++d) {
+    const float hd = bh[b * ND + d];
+    const bool p2 = P2;
+    const float inv_hd = 1.0f / hd;
+    const double inv_hd_d = 1.0 / (double)hd;
+    const int m0 = d == 0 ? BS + 1 : BS, m1 = d == 1 ? BS + 1 : BS;
+    const int ss = d == 0 ? 1 : (d == 1 ? PAD : PAD * PAD);
+    const FaceInfo& FL = fi[2 * d];
+    const FaceInfo& FH = fi[2 * d + 1];
+    const bool irr_lo = FL.kind != 1, irr_hi = FH.kind != 1;
+    const int nxl = (FINER && FL.kind == 3) ? FL.n1 * FL.n2 : 0, nxh = (FINER && FH.kind == 3) ? FH.n1 * FH.n2 : 0;
+    // ---- (1) fluxes.  Items [0, NFD): the uniform index space of k_reg_flux; faces whose stencil touches an
+    //      irregular block face are skipped there and re-enumerated, warp-uniformly, as items >= NFD:
+    //      [low block face, first internal face] if the low face is irregular, [last internal face, high block face]
+    //      if the high one is, then the fine faces of finer neighbours.
+    const int nlo = irr_lo ? 2 * FACE : 0, nhi = irr_hi ? 2 * FACE : 0;
+    for (int it = tid; it < NFD + nlo + nhi + nxl + nxh; it += NT) {
+      float po[NV], pn[NV], g0[NV], g1[NV];
+      float ho = hd, hn = hd, Do, Dn;
+      int fslot = it;
+      if (it < NFD + nlo + nhi) {
+        int cc[3];
+        if (it < NFD) {
+          cc[0] = it % m0; cc[1] = (it / m0) % m1; cc[2] = ND == 3 ? it / (m0 * m1) : 0;
+        } else {
+          int k = it - NFD;
+          int cdv;
+          if (k < nlo) cdv = k / FACE;                     // 0: low block face, 1: first internal face
+          else { k -= nlo; cdv = BS - 1 + k / FACE; }      // BS-1: last internal face, BS: high block face
+          int pq = k % FACE;
+          cc[0] = cc[1] = cc[2] = 0;
+          cc[d] = cdv;
+          cc[T1(d)] = pq % BS;
+          if (ND == 3) cc[T2(d)] = pq / BS;
+          fslot = cc[0] + m0 * (cc[1] + (ND == 3 ? m1 * cc[2] : 0));
+        }
+        const int cd = cc[d];
+        const int sn = pslot<ND, BS>(cc), so = sn - ss;
+        const bool irregular = (irr_lo && cd <= 1) || (irr_hi && cd >= BS - 1);
+        if (it < NFD) {
+          if (irregular) continue;
+          // uniform stencil: identical to k_reg_flux
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            float um = sP[v * NS + so - ss], uo = sP[v * NS + so], un = sP[v * NS + sn], up = sP[v * NS + sn + ss];
+            float fm = face_interp_f(um, uo, hd, hd, p2), fc = face_interp_f(uo, un, hd, hd, p2), fp = face_interp_f(un, up, hd, hd, p2);
+            g0[v] = p2 ? (fc - fm) * inv_hd : (fc - fm) / hd;
+            g1[v] = p2 ? (fp - fc) * inv_hd : (fp - fc) / hd;
+            po[v] = uo;
+            pn[v] = un;
+          }
+          Do = sD[so]; Dn = sD[sn];
+        } else if (cd >= 1 && cd <= BS - 1) {
+          // internal face next to an irregular block face: both cells are own cells, general gradients
+          int io[3] = {cc[0], cc[1], cc[2]};
+          io[d] -= 1;
+          hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, io, d, ss, hd, p2, inv_hd, g0);
+          hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, cc, d, ss, hd, p2, inv_hd, g1);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + so]; pn[v] = sP[v * NS + sn]; }
+          Do = sD[so]; Dn = sD[sn];
+        } else {
+          // block face: cd == 0 (low) or cd == BS (high)
+          const int side = cd == 0 ? 0 : 1;
+          const FaceInfo& F = side ? FH : FL;
+          if (FINER && F.kind == 3) continue;  // its 2^(ND-1) fine faces per cell are the extra items below
+          int io[3] = {cc[0], cc[1], cc[2]};
+          io[d] = side ? BS - 1 : 0;
+          const int own = pslot<ND, BS>(io);
+          float gown[NV], ghal[NV], pown[NV], phal[NV];
+          hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, io, d, ss, hd, p2, inv_hd, gown);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) pown[v] = sP[v * NS + own];
+          float Down = sD[own], Dhal, hh;
+          if (F.kind == 0) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { phal[v] = pown[v]; ghal[v] = gown[v]; }
+            Dhal = Down; hh = hd;
+          } else if (F.kind == 1) {  // same-level neighbour on this side, irregular face on the other side of the dim
+            int ih[3] = {cc[0], cc[1], cc[2]};
+            ih[d] = side ? BS : -1;
+            const int hs = pslot<ND, BS>(ih);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              float u0 = sP[v * NS + hs], u1 = sP[v * NS + (side ? hs + ss : hs - ss)];
+              float fnear = face_interp_f(u0, pown[v], hd, hd, p2), ffar = face_interp_f(u0, u1, hd, hd, p2);
+              float df = side ? ffar - fnear : fnear - ffar;
+              ghal[v] = p2 ? df * inv_hd : df / hd;
+              phal[v] = u0;
+            }
+            Dhal = sD[hs]; hh = hd;
+          } else {                   // coarser neighbour
+            int a1 = cc[T1(d)], a2 = ND == 3 ? cc[T2(d)] : 0;
+            int hr = (a2 >> 1) * F.n1 + (a1 >> 1);
+            const int hs = F.base + hr;
+            hyb_halo_grad<ND, BS, FINER, NV, NS>(sP, F, side, hr, d, hd, p2, ghal);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) phal[v] = sP[v * NS + hs];
+            Dhal = sD[hs]; hh = F.hn;
+          }
+          if (side) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { po[v] = pown[v]; g0[v] = gown[v]; pn[v] = phal[v]; g1[v] = ghal[v]; }
+            Do = Down; Dn = Dhal; ho = hd; hn = hh;
+          } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { po[v] = phal[v]; g0[v] = ghal[v]; pn[v] = pown[v]; g1[v] = gown[v]; }
+            Do = Dhal; Dn = Down; ho = hh; hn = hd;
+          }
+        }
+      } else {
+        // fine face k of a finer neighbour: halo fine cell k <-> own coarse cell (j1/2, j2/2)
+        const int kx = it - NFD - nlo - nhi;
+        const int side = kx >= nxl ? 1 : 0;
+        const FaceInfo& F = side ? FH : FL;
+        const int k = kx - (side ? nxl : 0);
+        int j1 = k % F.n1, j2 = k / F.n1;
+        int io[3] = {0, 0, 0};
+        io[d] = side ? BS - 1 : 0;
+        io[T1(d)] = j1 >> 1;
+        if (ND == 3) io[T2(d)] = j2 >> 1;
+        const int own = pslot<ND, BS>(io), hs = F.base + k;
+        float gown[NV], ghal[NV];
+        hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, io, d, ss, hd, p2, inv_hd, gown);
+        hyb_halo_grad<ND, BS, FINER, NV, NS>(sP, F, side, k, d, hd, p2, ghal);
+        if (side) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + own]; g0[v] = gown[v]; pn[v] = sP[v * NS + hs]; g1[v] = ghal[v]; }
+          Do = sD[own]; Dn = sD[hs]; ho = hd; hn = F.hn;
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + hs]; g0[v] = ghal[v]; pn[v] = sP[v * NS + own]; g1[v] = gown[v]; }
+          Do = sD[hs]; Dn = sD[own]; ho = F.hn; hn = hd;
+        }
+        fslot = NFD + side * (C::NX / 2) + k;
+      }
+      float pl[NV], pr[NV];
+      double F_[NV];
+      const bool fast = p2 && ho == hn;
+      muscl_face<NV>(po, pn, g0, g1, ho, hn, Do, Dn, true, false, pl, pr, fast);
+      if (FLUX == 0) {
+        hll_flux<ND>(fl, pl, pr, d, F_);
+      } else {
+        float Ff[NV];
+        rusanov_flux<ND>(fl, pl, pr, face_interp(Do, Dn, ho, hn), d, Ff);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) F_[v] = (double)Ff[v];
+      }
+      float ao = sqrtf(gr * clampT(po[1])), an = sqrtf(gr * clampT(pn[1]));
+      float ct = fabsf(face_interp_f(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), ho, hn, fast)) + face_interp_f(ao, an, ho, hn, fast);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sF[v * NFS + fslot] = F_[v];
+      sC[fslot] = ct;
+    }
+    __syncthreads();
+    // ---- (2) divergence
+#pragma unroll
+    for (int q = 0; q < RC::CPT; ++q) {
+      int l = tid + q * NT;
+      if (l < CPB) {
+        int ii[3];
+        split<ND, BS>(l, ii);
+        int lo = ii[0] + m0 * (ii[1] + (ND == 3 ? m1 * ii[2] : 0));
+        int hi = lo + (d == 0 ? 1 : (d == 1 ? m0 : m0 * m1));
+        double mh[NV], ml[NV];
+        float ch, cl;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          double* m = side ? mh : ml;
+          float& cm = side ? ch : cl;
+          const FaceInfo& F = side ? FH : FL;
+          bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+          if (inner || !FINER || F.kind != 3) {
+            int fs = side ? hi : lo;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) m[v] = sF[v * NFS + fs];
+            cm = sC[fs];
+          } else {
+            constexpr int CNT = ND == 3 ? 4 : 2;
+            const float w = 1.0f / (float)CNT;
+            int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
+#pragma unroll
+            for (int qq = 0; qq < CNT; ++qq) {
+              int fs = NFD + side * (C::NX / 2) + (ND == 3 ? (2 * a2 + (qq >> 1)) * F.n1 : 0) + 2 * a1 + (qq & 1);
+              if (FLUX == 0) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) m[v] = qq == 0 ? sF[v * NFS + fs] * (double)w : m[v] + sF[v * NFS + fs] * (double)w;
+              } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                  float t = (float)sF[v * NFS + fs] * w;
+                  m[v] = qq == 0 ? (double)t : (double)((float)m[v] + t);
+                }
+              }
+              cm = qq == 0 ? sC[fs] * w : cm + sC[fs] * w;
+            }
+          }
+        }
+        if (FLUX == 0) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) res[q][v] = (float)((double)res[q][v] - (mh[v] - ml[v]) * inv_hd_d);
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) res[q][v] = res[q][v] - ((float)mh[v] - (float)ml[v]) / hd;
+        }
+        cf[q] = cf[q] + (p2 ? (ch + cl) * inv_hd : (ch + cl) / hd);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < RC::CPT; ++q) {
+    int l = tid + q * NT;
+    if (l < CPB) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) R[(int64_t)v * N + cell0 + l] = res[q][v];
+      cfl[cell0 + l] = cf[q];
+    }
+  }
+}
+
+template <int ND, int BS, bool FINER, bool P2>
+int launch_hyb(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, int flux_kind, const float* P,
+               const float* S, float* R, float* cfl) {
+  using C = HybCfg<ND, BS, FINER>;
+  if (n == 0) return IBX_OK;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  if (flux_kind == 0)
+    k_hyb_flux<ND, BS, FINER, P2, 0><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
+  else
+    k_hyb_flux<ND, BS, FINER, P2, 1><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
+
 // lean sensor kernel for regular blocks: padded (BS+2)^ND tile of p, uniform loop (same bits as k_tile_sensor)
 template <int ND, int BS, bool P2>
 __global__ void __launch_bounds__(RegCfg<ND, BS>::NT)
@@ -748,8 +1154,17 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
   // fluxes: regular blocks (all neighbours same level) through the lean kernel, the rest through the general one
   if ((rc = D.all_pow2 ? launch_reg<ND, BS, true>(c, D, f, flux_kind, P, S, R, cfl) : launch_reg<ND, BS, false>(c, D, f, flux_kind, P, S, R, cfl))) return rc;
-  if ((rc = launch_pair<ND, BS, false>(c, D, nullptr, 0, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl, 1))) return rc;
-  if ((rc = launch_pair<ND, BS, true>(c, D, nullptr, 0, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl, 1))) return rc;
+  // IBX_TILE_GENERAL=1 routes the irregular blocks through the older general tile kernel (cross-check)
+  if (getenv("IBX_TILE_GENERAL") != nullptr) {
+    if ((rc = launch_pair<ND, BS, false>(c, D, nullptr, 0, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl, 1))) return rc;
+    if ((rc = launch_pair<ND, BS, true>(c, D, nullptr, 0, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl, 1))) return rc;
+  } else if (D.all_pow2) {
+    if ((rc = launch_hyb<ND, BS, false, true>(c, D, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl))) return rc;
+    if ((rc = launch_hyb<ND, BS, true, true>(c, D, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl))) return rc;
+  } else {
+    if ((rc = launch_hyb<ND, BS, false, false>(c, D, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl))) return rc;
+    if ((rc = launch_hyb<ND, BS, true, false>(c, D, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl))) return rc;
+  }
   return IBX_OK;
 }
 

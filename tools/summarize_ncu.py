@@ -1,0 +1,67 @@
+"""Turn ncu artefacts from gpurun_out/ into small text summaries under profiles/ (tracked)."""
+import collections, csv, subprocess, sys, os
+
+def launches(path, out):
+    rows = list(csv.reader(open(path)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[hdr]; ki = H.index("Kernel Name"); vi = H.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi: continue
+        agg.setdefault(r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", ""), []).append(float(r[vi].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    with open(out, "w") as fh:
+        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+        fh.write(f"# source: {path}\n")
+        for k, v in agg.items():
+            fh.write(f"{k:40s} launches={len(v):3d} avg_ms={sum(v)/len(v)/1e6:9.3f} share={sum(v)/tot*100:5.1f}%\n")
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "lts__t_bytes.sum", "sass__inst_executed_shared_loads", "sass__inst_executed_global_loads"]
+
+def report(rep, out, cells=None):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, U, V = rows[0], rows[1], rows[2]
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    srows = list(csv.reader(src.splitlines()))
+    SH = srows[1]
+    si, ei = SH.index("Source"), SH.index("Instructions Executed")
+    cols = [(i, h) for i, h in enumerate(SH) if h.startswith("stall_") and "Not Issued" not in h]
+    op, st, tot = collections.Counter(), collections.Counter(), 0
+    for r in srows[2:]:
+        if len(r) <= ei: continue
+        m = r[si].strip().split()
+        if not m: continue
+        mn = (m[0] if not m[0].startswith("@") else m[1]).split(".")[0]
+        n = int(r[ei]); op[mn] += n; tot += n
+        for i, h in cols: st[h] += int(r[i])
+    with open(out, "w") as fh:
+        fh.write(f"# ncu --set full --clock-control none --import-source on; source: {rep}\n")
+        fh.write(f"kernel: {V[H.index('Kernel Name')]}\n")
+        for w in WANT:
+            if w in H:
+                i = H.index(w); fh.write(f"{w:72s} {U[i]:>16s} {V[i]}\n")
+        fh.write(f"SASS instructions in kernel: {len(srows) - 2}\n")
+        if cells:
+            fh.write(f"thread-instructions per cell: {tot * 32 / cells:.1f}  (cells in this launch: {cells})\n")
+            i = H.index("dram__bytes_read.sum"); j = H.index("dram__bytes_write.sum")
+            def val(k):
+                x = float(V[k].replace(",", "")); u = U[k]
+                return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
+            fh.write(f"DRAM traffic per cell: {(val(i) + val(j)) / cells:.1f} B\n")
+        fh.write("opcode mix (share of executed warp instructions):\n")
+        for k, v in op.most_common(16): fh.write(f"  {k:8s} {v / tot * 100:5.1f}%\n")
+        S = sum(st.values()) or 1
+        fh.write("warp stall samples: " + ", ".join(f"{k[6:]} {v / S * 100:.1f}%" for k, v in st.most_common(9)) + "\n")
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    if cmd == "launches": launches(sys.argv[2], sys.argv[3])
+    else: report(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
