@@ -170,7 +170,7 @@ def run_ours(args):
     msh = build_mesh(ib, radius, h)
     fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
     gdom = ib.Domain(msh, max_partition_size=len(msh), hypercube_families=fams, build_partitions=False,
-                     build_surfaces=False, upload=False)
+                     build_surfaces=False, upload=False, for_rank=(rank, world) if world > 1 else None)
     n_global = len(gdom)
     if world > 1:
         def gather(obj):
@@ -185,10 +185,9 @@ def run_ours(args):
         dist.broadcast_object_list(obj, src=0)
         ident = np.frombuffer(obj[0], np.uint8).copy()
         ib._lib.call("ibx_comm_init", ctx, rank, world, ib._lib.ptr(ident))
-        l2g = dom.shard_info["local_to_global"]
         n_owned = dom.shard_info["n_owned"]
-        centers = gdom.cells()[0][l2g]
         del gdom
+        centers = dom.cells()[0]
     else:
         dom, n_owned = gdom, n_global
         centers = dom.cells()[0]

@@ -573,7 +573,7 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
 }
 
 static void ghosts_hcube(const ibx_domain& D, const std::vector<std::pair<int, int>>& faces, float glr,
-                         std::vector<int32_t>& ghosts, std::vector<float>& projs) {
+                         std::vector<int32_t>& ghosts, std::vector<float>& projs, int64_t r0, int64_t r1) {
   // src/ImmersedBoundary.jl:258-305
   int nd = D.nd;
   const ibx_mesh& m = *D.mesh;
@@ -583,7 +583,7 @@ static void ghosts_hcube(const ibx_domain& D, const std::vector<std::pair<int, i
   std::vector<uint8_t> mask(N, 0);
   std::vector<int8_t> which(N, -1);
 #pragma omp parallel for schedule(static)
-  for (int64_t i = 0; i < N; ++i) {
+  for (int64_t i = r0; i < r1; ++i) {
     float best = INFINITY;
     float lim = diam_of(W + i * nd, nd) * glr;
     for (size_t f = 0; f < faces.size(); ++f) {
@@ -595,7 +595,7 @@ static void ghosts_hcube(const ibx_domain& D, const std::vector<std::pair<int, i
       if (ds < lim) mask[i] = 1;
     }
   }
-  for (int64_t i = 0; i < N; ++i)
+  for (int64_t i = r0; i < r1; ++i)
     if (mask[i]) {
       ghosts.push_back((int32_t)i);
       int dim = faces[which[i]].first;
@@ -605,7 +605,7 @@ static void ghosts_hcube(const ibx_domain& D, const std::vector<std::pair<int, i
 }
 
 static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr, std::vector<int32_t>& ghosts,
-                           std::vector<float>& projs) {
+                           std::vector<float>& projs, int64_t r0, int64_t r1) {
   // src/ImmersedBoundary.jl:194-230
   int nd = D.nd;
   const float* C = D.centers.data();
@@ -620,7 +620,7 @@ static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr,
     std::vector<float>& lp = tproj[omp_get_thread_num()];
     std::vector<int32_t>& lg = tghost[omp_get_thread_num()];
 #pragma omp for schedule(static)
-    for (int64_t i = 0; i < N; ++i) {
+    for (int64_t i = r0; i < r1; ++i) {
       double x[3];
       for (int d = 0; d < nd; ++d) x[d] = C[i * nd + d];
       float diam = diam_of(W + i * nd, nd);
@@ -687,11 +687,15 @@ using namespace ibx;
 
 extern "C" {
 
-int ibx_domain_build(const ibx_mesh* mh, int64_t max_partition_size, int skirt_depth, float ghost_layer_ratio, int nfam,
-                     const char* const* fam_names, const int* fam_ptr, const int* fam_dim, const int* fam_front,
-                     int build_partitions_flag, int build_surfaces, ibx_domain** out) {
+static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int skirt_depth, float ghost_layer_ratio, int nfam,
+                             const char* const* fam_names, const int* fam_ptr, const int* fam_dim, const int* fam_front,
+                             int build_partitions_flag, int build_surfaces, int rank, int nranks, ibx_domain** out) {
   IBX_TRY
   auto m = lookup_mesh(mh);
+  IBX_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank out of range");
+  // ghosts (and their donor stencils) are only searched among the cells of this rank's block range
+  const int64_t g_r0 = (m->nblocks() * rank / nranks) * m->cells_per_block();
+  const int64_t g_r1 = (m->nblocks() * (rank + 1) / nranks) * m->cells_per_block();
   IBX_REQUIRE(max_partition_size >= 1, "max_partition_size must be positive");
   IBX_REQUIRE(m->ncells() < (int64_t)2147483647, "more than 2^31-1 cells: Int64 tables are not implemented");
   auto D = std::make_shared<ibx_domain>();
@@ -716,7 +720,7 @@ int ibx_domain_build(const ibx_mesh* mh, int64_t max_partition_size, int skirt_d
     }
     std::vector<int32_t> ghosts;
     std::vector<float> projs;
-    ghosts_hcube(*D, faces, ghost_layer_ratio, ghosts, projs);
+    ghosts_hcube(*D, faces, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
     BoundaryFamily fam;
     fam.name = fam_names[f];
     build_boundary(*D, bi, ghosts, projs, max_partition_size, ghost_layer_ratio, fam);
@@ -726,7 +730,7 @@ int ibx_domain_build(const ibx_mesh* mh, int64_t max_partition_size, int skirt_d
     const ibx_dfield& df = *m->surf_fields[s];
     std::vector<int32_t> ghosts;
     std::vector<float> projs;
-    ghosts_surface(*D, df, ghost_layer_ratio, ghosts, projs);
+    ghosts_surface(*D, df, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
     BoundaryFamily fam;
     fam.name = m->surf_names[s];
     build_boundary(*D, bi, ghosts, projs, max_partition_size, ghost_layer_ratio, fam);
@@ -774,6 +778,20 @@ int ibx_domain_build(const ibx_mesh* mh, int64_t max_partition_size, int skirt_d
   *out = D.get();
   return IBX_OK;
   IBX_CATCH
+}
+
+int ibx_domain_build(const ibx_mesh* mh, int64_t max_partition_size, int skirt_depth, float ghost_layer_ratio, int nfam,
+                     const char* const* fam_names, const int* fam_ptr, const int* fam_dim, const int* fam_front,
+                     int build_partitions_flag, int build_surfaces, ibx_domain** out) {
+  return domain_build_impl(mh, max_partition_size, skirt_depth, ghost_layer_ratio, nfam, fam_names, fam_ptr, fam_dim, fam_front,
+                           build_partitions_flag, build_surfaces, 0, 1, out);
+}
+
+int ibx_domain_build_for_rank(const ibx_mesh* mh, float ghost_layer_ratio, int nfam, const char* const* fam_names,
+                              const int* fam_ptr, const int* fam_dim, const int* fam_front, int rank, int nranks,
+                              ibx_domain** out) {
+  return domain_build_impl(mh, (int64_t)1 << 40, 2, ghost_layer_ratio, nfam, fam_names, fam_ptr, fam_dim, fam_front, 0, 0, rank,
+                           nranks, out);
 }
 
 int ibx_domain_free(ibx_domain* d) {

@@ -397,7 +397,8 @@ class Domain:
     on a machine without a GPU)."""
 
     def __init__(self, msh, max_partition_size=100_000, partition_skirt_depth=2, ghost_layer_ratio=F32(1.5),
-                 hypercube_families=(), build_partitions=True, build_surfaces=True, upload=True, _handle=None):
+                 hypercube_families=(), build_partitions=True, build_surfaces=True, upload=True, _handle=None,
+                 for_rank=None):
         self.mesh = msh
         self._h = C.c_void_p()
         fams = list(hypercube_families)
@@ -415,9 +416,13 @@ class Domain:
             fptr[i + 1] = len(dims)
         dims = np.asarray(dims if dims else [0], dtype=np.int32)
         fronts = np.asarray(fronts if fronts else [0], dtype=np.int32)
-        call("ibx_domain_build", msh._h, int(max_partition_size), int(partition_skirt_depth), float(ghost_layer_ratio),
-             len(fams), names, ptr(fptr), ptr(dims), ptr(fronts), int(build_partitions), int(build_surfaces),
-             C.byref(self._h))
+        if for_rank is not None:  # (rank, nranks): ghosts only for that rank's block range, input of .shard()
+            call("ibx_domain_build_for_rank", msh._h, float(ghost_layer_ratio), len(fams), names, ptr(fptr), ptr(dims),
+                 ptr(fronts), int(for_rank[0]), int(for_rank[1]), C.byref(self._h))
+        else:
+            call("ibx_domain_build", msh._h, int(max_partition_size), int(partition_skirt_depth), float(ghost_layer_ratio),
+                 len(fams), names, ptr(fptr), ptr(dims), ptr(fronts), int(build_partitions), int(build_surfaces),
+                 C.byref(self._h))
         self._describe(max_partition_size, partition_skirt_depth, ghost_layer_ratio, fams)
         if upload:
             self.upload()

@@ -121,6 +121,12 @@ int ibx_mesh_cells(const ibx_mesh* m, float* centers, float* widths);
 int ibx_domain_build(const ibx_mesh* m, int64_t max_partition_size, int skirt_depth, float ghost_layer_ratio,
                      int nfam, const char* const* fam_names, const int* fam_ptr, const int* fam_dim,
                      const int* fam_front, int build_partitions, int build_surfaces, ibx_domain** out);
+/* Same global cell numbering and block connectivity, but ghosts / image stencils are only built for the cells of
+ * `rank`'s contiguous block range: the input of ibx_domain_shard when every rank builds its own tables (no
+ * partition tables, no surfaces).  Cost: O(all blocks) + O(owned cells). */
+int ibx_domain_build_for_rank(const ibx_mesh* m, float ghost_layer_ratio, int nfam, const char* const* fam_names,
+                              const int* fam_ptr, const int* fam_dim, const int* fam_front, int rank, int nranks,
+                              ibx_domain** out);
 int ibx_domain_free(ibx_domain* d);
 int ibx_domain_info(const ibx_domain* d, int* nd, int64_t* ncells, int64_t* nfaces, int* npartitions,
                     int* nboundaries, int* nsurfaces);
