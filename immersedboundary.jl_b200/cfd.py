@@ -50,10 +50,11 @@ def speed_of_sound(fluid, T):
 def inviscid_fluxes(fluid, PL, PR, *args):
     """``inviscid_fluxes(fluid, PL, PR, dim)`` (HLL, ``src/cfd.jl:459-508``) or
     ``inviscid_fluxes(fluid, PL, PR, nuL, nuR, dim)`` (sensor-Rusanov, ``:516-554``); ``dim`` 0-based."""
-    F = _like(PL)
     if len(args) == 1:
+        F = DeviceArray(PL.rows, PL.cols, PL.vector, f64=True)  # the reference returns Float64 here (src/cfd.jl:504-507)
         call("ibx_inviscid_fluxes_hll", context(), fluid.c, PL.h, PR.h, int(args[0]), F.h)
     else:
+        F = _like(PL)
         nuL, nuR, dim = args
         call("ibx_inviscid_fluxes_sensor", context(), fluid.c, PL.h, PR.h, nuL.h, nuR.h, int(dim), F.h)
     return F

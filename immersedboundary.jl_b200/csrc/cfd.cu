@@ -63,9 +63,9 @@ __global__ void k_sound(ibx_fluid f, const float* __restrict__ T, float* __restr
 }
 
 // HLL (src/cfd.jl:459-508) along Cartesian dim
-template <int ND>
+template <int ND, class TO>
 __global__ void k_hll(ibx_fluid f, const float* __restrict__ PL, const float* __restrict__ PR, int dim,
-                      float* __restrict__ F, int64_t n) {
+                      TO* __restrict__ F, int64_t n) {
   constexpr int NV = 2 + ND;
   float gr = f.gamma * f.R;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -90,7 +90,7 @@ __global__ void k_hll(ibx_fluid f, const float* __restrict__ PL, const float* __
     double SL = fmax((double)(uL + aL), 0.0);
 #pragma unroll
     for (int v = 0; v < NV; ++v)
-      F[(int64_t)v * n + i] = (float)((SL * (double)fl[v] - SR * (double)fr[v] + SR * SL * (double)(qr[v] - ql[v])) / (SL - SR));
+      F[(int64_t)v * n + i] = (TO)((SL * (double)fl[v] - SR * (double)fr[v] + SR * SL * (double)(qr[v] - ql[v])) / (SL - SR));
   }
 }
 
@@ -281,12 +281,15 @@ int ibx_inviscid_fluxes_hll(ibx_ctx* c, ibx_fluid f, ibx_array PL, ibx_array PR,
   CHECK_CTX(c);
   GET_ARR(L, PL);
   GET_ARR(R, PR);
-  GET_ARR(O, F);
+  GET_ARR_ANY(O, F);  // float64 output keeps the reference's promotion (src/cfd.jl:504-507); float32 rounds once
   SHAPE(L.rows == R.rows && L.rows == O.rows && L.cols == R.cols && L.cols == O.cols && (L.cols == 4 || L.cols == 5),
         "PL, PR, F must be nfaces x (2 + nd)");
   if (dim < 0 || dim >= L.cols - 2) return fail(IBX_ERR_ARG, "ibx_inviscid_fluxes_hll: dim out of range");
-  if (L.cols == 4) k_hll<2><<<GRID(L.rows)>>>(f, L.p, R.p, dim, O.p, L.rows);
-  else k_hll<3><<<GRID(L.rows)>>>(f, L.p, R.p, dim, O.p, L.rows);
+  if (O.f64) {
+    if (L.cols == 4) k_hll<2, double><<<GRID(L.rows)>>>(f, L.p, R.p, dim, (double*)O.p, L.rows);
+    else k_hll<3, double><<<GRID(L.rows)>>>(f, L.p, R.p, dim, (double*)O.p, L.rows);
+  } else if (L.cols == 4) k_hll<2, float><<<GRID(L.rows)>>>(f, L.p, R.p, dim, O.p, L.rows);
+  else k_hll<3, float><<<GRID(L.rows)>>>(f, L.p, R.p, dim, O.p, L.rows);
   LAUNCH_CHECK();
   return IBX_OK;
 }

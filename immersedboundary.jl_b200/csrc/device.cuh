@@ -15,7 +15,7 @@ struct ibx_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_ready = nullptr;
   int64_t launches = 0;
   bool poisoned = false;
-  struct Arr { float* p; int64_t rows, cols; };
+  struct Arr { float* p; int64_t rows, cols; bool f64; };  // f64: the buffer holds doubles (HLL fluxes, src/cfd.jl:504-507)
   std::unordered_map<int64_t, Arr> arrays;
   int64_t next_handle = 1;
   std::mutex mu;
@@ -54,9 +54,13 @@ float* ensure_scratch(ibx_ctx* c, int64_t nfloats);
     cudaSetDevice((c)->device);                                                             \
   } while (0)
 
-#define GET_ARR(var, h)                                                                              \
+#define GET_ARR_ANY(var, h)                                                                          \
   ibx_ctx::Arr var;                                                                                  \
   if (!ibx::get_array(c, (h), var)) return ibx::fail(IBX_ERR_ARG, std::string(__func__) + ": invalid array handle " #h)
+
+#define GET_ARR(var, h)                                                                              \
+  GET_ARR_ANY(var, h);                                                                               \
+  if (var.f64) return ibx::fail(IBX_ERR_UNSUPPORTED, std::string(__func__) + ": float64 array passed as " #h " (only the HLL flux, green_gauss and the elementwise entry points take float64)")
 
 #define GET_DOM(D, d)                                                                             \
   ibx_domain* D##_p = ibx::find_domain(d);                                                        \

@@ -97,6 +97,77 @@ __global__ void k_green_gauss(const float* __restrict__ uf, int64_t nf, const fl
   }
 }
 
+// Float64 variant: what Julia does when `uf` is the Float64 HLL flux (weights and spacing promote)
+__global__ void k_green_gauss64(const double* __restrict__ uf, int64_t nf, const float* __restrict__ sp,
+                                const int32_t* __restrict__ lptr, const int32_t* __restrict__ lidx,
+                                const int32_t* __restrict__ rptr, const int32_t* __restrict__ ridx,
+                                double* __restrict__ out, int64_t n, int cols, int unsigned_) {
+  int64_t tot = n * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell = t % n, col = t / n;
+    const double* ufc = uf + col * nf;
+    double side[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int32_t* ptr = s ? rptr : lptr;
+      const int32_t* idx = s ? ridx : lidx;
+      int32_t b = ptr[cell], e = ptr[cell + 1];
+      double acc = 0.0;
+      if (e > b) {
+        double w = (double)(1.0f / (float)(e - b));
+        acc = ufc[idx[b]] * w;
+        for (int32_t k = b + 1; k < e; ++k) acc = acc + ufc[idx[k]] * w;
+      }
+      side[s] = acc;
+    }
+    out[t] = (unsigned_ ? (side[1] + side[0]) : (side[1] - side[0])) / (double)sp[cell];
+  }
+}
+
+struct AnyPtr {
+  void* p;
+  int f64;
+};
+__device__ __forceinline__ double ldany(AnyPtr a, int64_t i) { return a.f64 ? ((const double*)a.p)[i] : (double)((const float*)a.p)[i]; }
+__device__ __forceinline__ void stany(AnyPtr a, int64_t i, double v) {
+  if (a.f64) ((double*)a.p)[i] = v; else ((float*)a.p)[i] = (float)v;
+}
+__device__ __forceinline__ double binop64(int op, double x, double y) {
+  switch (op) {
+    case 0: return x + y;
+    case 1: return x - y;
+    case 2: return x * y;
+    case 3: return x / y;
+    case 4: return fmax(x, y);
+    default: return fmin(x, y);
+  }
+}
+// elementwise with at least one Float64 operand: Julia promotes to Float64, then converts on assignment
+__global__ void k_ew_binary_any(int op, AnyPtr a, int acols, AnyPtr b, int bcols, AnyPtr out, int64_t n, int cols) {
+  int64_t tot = n * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = t % n, col = t / n;
+    stany(out, t, binop64(op, ldany(a, (acols == 1 ? 0 : col) * n + i), ldany(b, (bcols == 1 ? 0 : col) * n + i)));
+  }
+}
+__global__ void k_ew_scalar_any(int op, AnyPtr a, double s, int scalar_first, AnyPtr out, int64_t tot) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x)
+    stany(out, t, scalar_first ? binop64(op, s, ldany(a, t)) : binop64(op, ldany(a, t), s));
+}
+__global__ void k_ew_unary_any(int op, AnyPtr a, AnyPtr out, int64_t tot) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    double x = ldany(a, t), r;
+    switch (op) {
+      case 0: r = fabs(x); break;
+      case 1: r = -x; break;
+      case 2: r = sqrt(x); break;
+      case 3: r = (double)((x > 0.0) - (x < 0.0)); break;
+      default: r = 1.0 / x; break;
+    }
+    stany(out, t, r);
+  }
+}
+
 __device__ __forceinline__ float face_value(const float* __restrict__ u, const float* __restrict__ sp,
                                             const int32_t* __restrict__ own, const int32_t* __restrict__ nei, int32_t f) {
   int32_t o = own[f], n = nei[f];
@@ -529,12 +600,19 @@ static int gg_impl(ibx_ctx* c, const ibx_domain* d, int p, int dim, ibx_array uf
   GET_DOM(D, d);
   PART(P, D, p);
   DIMCHK(D, dim);
-  GET_ARR(U, uf);
-  GET_ARR(O, out);
+  GET_ARR_ANY(U, uf);
+  GET_ARR_ANY(O, out);
   const FaceTable& T = P.dims[dim];
   int64_t n = (int64_t)P.domain.size(), nf = (int64_t)T.owners.size();
   if (U.rows != nf || O.rows != n || O.cols != U.cols)
     return fail(IBX_ERR_ARG, std::string(fn) + ": uf must be nfaces x nv and out n_domain x nv");
+  if (U.f64 != O.f64) return fail(IBX_ERR_ARG, std::string(fn) + ": uf and out must have the same element type");
+  if (U.f64) {
+    k_green_gauss64<<<GRID(n * U.cols)>>>((const double*)U.p, nf, P.d_spacing + (int64_t)dim * n, T.d_lptr, T.d_lidx, T.d_rptr, T.d_ridx,
+                                          (double*)O.p, n, (int)U.cols, uns);
+    LAUNCH_CHECK();
+    return IBX_OK;
+  }
   k_green_gauss<<<GRID(n * U.cols)>>>(U.p, nf, P.d_spacing + (int64_t)dim * n, T.d_lptr, T.d_lidx, T.d_rptr, T.d_ridx, O.p, n, (int)U.cols, uns);
   LAUNCH_CHECK();
   return IBX_OK;
@@ -733,13 +811,18 @@ int ibx_surface_integral(ibx_ctx* c, const ibx_domain* d, int s, ibx_array u, fl
 // ------------------------------------------------------------------ elementwise + reductions
 int ibx_ew_binary(ibx_ctx* c, int op, ibx_array a, ibx_array b, ibx_array out) {
   CHECK_CTX(c);
-  GET_ARR(A, a);
-  GET_ARR(B, b);
-  GET_ARR(O, out);
+  GET_ARR_ANY(A, a);
+  GET_ARR_ANY(B, b);
+  GET_ARR_ANY(O, out);
   if (op < 0 || op > 5) return fail(IBX_ERR_ARG, "ibx_ew_binary: unknown op");
   int cols = (int)std::max(A.cols, B.cols);
   SHAPE(A.rows == B.rows && O.rows == A.rows && O.cols == cols && (A.cols == cols || A.cols == 1) && (B.cols == cols || B.cols == 1),
         "operands must have equal rows; a 1-column operand broadcasts over columns");
+  if (A.f64 || B.f64 || O.f64) {
+    k_ew_binary_any<<<GRID(A.rows * cols)>>>(op, AnyPtr{A.p, A.f64}, (int)A.cols, AnyPtr{B.p, B.f64}, (int)B.cols, AnyPtr{O.p, O.f64}, A.rows, cols);
+    LAUNCH_CHECK();
+    return IBX_OK;
+  }
   k_ew_binary<<<GRID(A.rows * cols)>>>(op, A.p, (int)A.cols, B.p, (int)B.cols, O.p, A.rows, cols);
   LAUNCH_CHECK();
   return IBX_OK;
@@ -747,10 +830,15 @@ int ibx_ew_binary(ibx_ctx* c, int op, ibx_array a, ibx_array b, ibx_array out) {
 
 int ibx_ew_scalar(ibx_ctx* c, int op, ibx_array a, float s, int scalar_first, ibx_array out) {
   CHECK_CTX(c);
-  GET_ARR(A, a);
-  GET_ARR(O, out);
+  GET_ARR_ANY(A, a);
+  GET_ARR_ANY(O, out);
   if (op < 0 || op > 5) return fail(IBX_ERR_ARG, "ibx_ew_scalar: unknown op");
   SHAPE(O.rows == A.rows && O.cols == A.cols, "out must match a");
+  if (A.f64 || O.f64) {
+    k_ew_scalar_any<<<GRID(A.rows * A.cols)>>>(op, AnyPtr{A.p, A.f64}, (double)s, scalar_first, AnyPtr{O.p, O.f64}, A.rows * A.cols);
+    LAUNCH_CHECK();
+    return IBX_OK;
+  }
   k_ew_scalar<<<GRID(A.rows * A.cols)>>>(op, A.p, s, scalar_first, O.p, A.rows * A.cols);
   LAUNCH_CHECK();
   return IBX_OK;
@@ -758,10 +846,15 @@ int ibx_ew_scalar(ibx_ctx* c, int op, ibx_array a, float s, int scalar_first, ib
 
 int ibx_ew_unary(ibx_ctx* c, int op, ibx_array a, ibx_array out) {
   CHECK_CTX(c);
-  GET_ARR(A, a);
-  GET_ARR(O, out);
+  GET_ARR_ANY(A, a);
+  GET_ARR_ANY(O, out);
   if (op < 0 || op > 4) return fail(IBX_ERR_ARG, "ibx_ew_unary: unknown op");
   SHAPE(O.rows == A.rows && O.cols == A.cols, "out must match a");
+  if (A.f64 || O.f64) {
+    k_ew_unary_any<<<GRID(A.rows * A.cols)>>>(op, AnyPtr{A.p, A.f64}, AnyPtr{O.p, O.f64}, A.rows * A.cols);
+    LAUNCH_CHECK();
+    return IBX_OK;
+  }
   k_ew_unary<<<GRID(A.rows * A.cols)>>>(op, A.p, O.p, A.rows * A.cols);
   LAUNCH_CHECK();
   return IBX_OK;

@@ -151,17 +151,36 @@ int ibx_timer_stop(ibx_ctx* c, float* ms) {
   return IBX_OK;
 }
 
-int ibx_array_alloc(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out) {
+static int alloc_impl(ibx_ctx* c, int64_t rows, int64_t cols, bool f64, ibx_array* out) {
   CHECK_CTX(c);
   if (rows < 0 || cols < 1) return fail(IBX_ERR_ARG, "ibx_array_alloc: rows >= 0 and cols >= 1 required");
   float* p = nullptr;
-  size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * sizeof(float);
+  size_t bytes = std::max<size_t>((size_t)rows * cols, 1) * (f64 ? sizeof(double) : sizeof(float));
   CU(cudaMalloc((void**)&p, bytes));
   CU(cudaMemsetAsync(p, 0, bytes, c->stream));
   std::lock_guard<std::mutex> lk(c->mu);
   int64_t h = c->next_handle++;
-  c->arrays[h] = {p, rows, cols};
+  c->arrays[h] = {p, rows, cols, f64};
   *out = h;
+  return IBX_OK;
+}
+
+int ibx_array_alloc(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out) { return alloc_impl(c, rows, cols, false, out); }
+int ibx_array_alloc_f64(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out) { return alloc_impl(c, rows, cols, true, out); }
+
+int ibx_array_is_f64(ibx_ctx* c, ibx_array a, int* out) {
+  CHECK_CTX(c);
+  GET_ARR_ANY(A, a);
+  *out = A.f64;
+  return IBX_OK;
+}
+
+int ibx_array_download_f64(ibx_ctx* c, ibx_array a, double* host) {
+  CHECK_CTX(c);
+  GET_ARR_ANY(A, a);
+  if (!A.f64) return fail(IBX_ERR_ARG, "ibx_array_download_f64: array is float32");
+  CU(cudaMemcpyAsync(host, A.p, (size_t)A.rows * A.cols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return IBX_OK;
 }
 
@@ -179,7 +198,7 @@ int ibx_array_free(ibx_ctx* c, ibx_array a) {
 
 int ibx_array_shape(ibx_ctx* c, ibx_array a, int64_t* rows, int64_t* cols) {
   CHECK_CTX(c);
-  GET_ARR(A, a);
+  GET_ARR_ANY(A, a);
   *rows = A.rows;
   *cols = A.cols;
   return IBX_OK;
@@ -203,10 +222,10 @@ int ibx_array_download(ibx_ctx* c, ibx_array a, float* host) {
 
 int ibx_array_copy(ibx_ctx* c, ibx_array dst, ibx_array src) {
   CHECK_CTX(c);
-  GET_ARR(A, dst);
-  GET_ARR(B, src);
-  if (A.rows != B.rows || A.cols != B.cols) return fail(IBX_ERR_ARG, "ibx_array_copy: shape mismatch");
-  CU(cudaMemcpyAsync(A.p, B.p, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  GET_ARR_ANY(A, dst);
+  GET_ARR_ANY(B, src);
+  if (A.rows != B.rows || A.cols != B.cols || A.f64 != B.f64) return fail(IBX_ERR_ARG, "ibx_array_copy: shape or element type mismatch");
+  CU(cudaMemcpyAsync(A.p, B.p, (size_t)A.rows * A.cols * (A.f64 ? sizeof(double) : sizeof(float)), cudaMemcpyDeviceToDevice, c->stream));
   return IBX_OK;
 }
 

@@ -52,12 +52,13 @@ class DeviceArray:
     """
     __array_priority__ = 1000
 
-    def __init__(self, rows, cols=1, vector=None, _handle=None):
+    def __init__(self, rows, cols=1, vector=None, _handle=None, f64=False):
         self.rows, self.cols = int(rows), int(cols)
         self.vector = (self.cols == 1) if vector is None else vector  # 1-D (N,) vs (N, 1)
+        self.f64 = bool(f64)  # Float64 payload: the HLL flux and what is derived from it (src/cfd.jl:504-507)
         if _handle is None:
             h = C.c_int64()
-            call("ibx_array_alloc", context(), self.rows, self.cols, C.byref(h))
+            call("ibx_array_alloc_f64" if f64 else "ibx_array_alloc", context(), self.rows, self.cols, C.byref(h))
             _handle = h.value
         self.h = _handle
 
@@ -81,16 +82,17 @@ class DeviceArray:
         return self
 
     def to_host(self):
-        out = np.zeros((self.rows, self.cols), dtype=F32, order="F")
-        call("ibx_array_download", context(), self.h, ptr(out))
+        out = np.zeros((self.rows, self.cols), dtype=np.float64 if self.f64 else F32, order="F")
+        call("ibx_array_download_f64" if self.f64 else "ibx_array_download", context(), self.h, ptr(out))
         return out[:, 0].copy() if self.vector else out
 
     @property
     def shape(self):
         return (self.rows,) if self.vector else (self.rows, self.cols)
 
-    def like(self, cols=None, vector=None):
-        return DeviceArray(self.rows, self.cols if cols is None else cols, self.vector if vector is None else vector)
+    def like(self, cols=None, vector=None, f64=None):
+        return DeviceArray(self.rows, self.cols if cols is None else cols, self.vector if vector is None else vector,
+                           f64=self.f64 if f64 is None else f64)
 
     def copy(self):
         out = self.like()
@@ -114,7 +116,7 @@ class DeviceArray:
         if isinstance(other, DeviceArray):
             a, b = (other, self) if reverse else (self, other)
             big = a if a.cols >= b.cols else b
-            out = out or big.like()
+            out = out or big.like(f64=a.f64 or b.f64)  # Julia promotion; in-place forms keep the target type
             call("ibx_ew_binary", context(), op, a.h, b.h, out.h)
             return out
         out = out or self.like()
@@ -568,7 +570,7 @@ def volume_integral(dom, A):
 
 # --------------------------------------------------------------------------------- grid operators
 def _op(name, part, dim, u, rows, cols=None, vector=None):
-    out = DeviceArray(rows, u.cols if cols is None else cols, u.vector if vector is None else vector)
+    out = DeviceArray(rows, u.cols if cols is None else cols, u.vector if vector is None else vector, f64=u.f64)
     call(name, context(), part.dom._h, part.p, int(dim), u.h, out.h)
     return out
 

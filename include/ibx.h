@@ -185,6 +185,13 @@ int ibx_timer_start(ibx_ctx* c);
 int ibx_timer_stop(ibx_ctx* c, float* ms);
 
 int ibx_array_alloc(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out);
+/* Float64 arrays exist for one reason: the reference's HLL flux is Float64 (src/cfd.jl:504-507) and so is every
+ * Green-Gauss sum taken of it.  Accepted by: ibx_inviscid_fluxes_hll (F), ibx_green_gauss / ibx_unsigned_green_gauss
+ * (uf and out), ibx_ew_binary / ibx_ew_scalar / ibx_ew_unary (any operand; Julia promotion, conversion on store),
+ * ibx_array_copy / shape / free.  Every other entry point rejects them with IBX_ERR_UNSUPPORTED. */
+int ibx_array_alloc_f64(ibx_ctx* c, int64_t rows, int64_t cols, ibx_array* out);
+int ibx_array_is_f64(ibx_ctx* c, ibx_array a, int* out);
+int ibx_array_download_f64(ibx_ctx* c, ibx_array a, double* host);
 int ibx_array_free(ibx_ctx* c, ibx_array a);
 int ibx_array_shape(ibx_ctx* c, ibx_array a, int64_t* rows, int64_t* cols);
 int ibx_array_upload(ibx_ctx* c, ibx_array a, const float* host);        /* column-major rows x cols */

@@ -76,8 +76,11 @@ def test_cfd_kernels(ib, oracle):
         dnu = ib.DeviceArray.from_host(nu)
         for dim in range(nd):
             F = cfd.inviscid_fluxes_hll(ofl, P, PR, dim)
-            dF = ib.inviscid_fluxes(fl, dP, dPR, dim).to_host()
-            assert np.array_equal(dF, F.astype(F32))  # same float64 evaluation, rounded once on store
+            dF = ib.inviscid_fluxes(fl, dP, dPR, dim)
+            assert dF.f64 and np.array_equal(dF.to_host(), F)  # Float64 like the reference (src/cfd.jl:504-507)
+            dF32 = ib.DeviceArray(n, nd + 2, False)
+            ib._lib.call("ibx_inviscid_fluxes_hll", ib.context(), fl.c, dP.h, dPR.h, dim, dF32.h)
+            assert np.array_equal(dF32.to_host(), F.astype(F32))  # float32 output: same evaluation rounded once
             Fs = cfd.inviscid_fluxes_sensor(ofl, P, PR, nu, nu * F32(0.5), dim)
             dFs = ib.inviscid_fluxes(fl, dP, dPR, dnu, dnu * 0.5, dim).to_host()
             assert np.array_equal(dFs, Fs)
