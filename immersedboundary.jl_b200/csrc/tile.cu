@@ -491,6 +491,19 @@ struct RegCfg {
   static constexpr size_t SMEM = sizeof(double) * (size_t)NV * NFD + sizeof(float) * ((size_t)(NV + 1) * TS + NFD);
 };
 
+// it -> (c0, c1, c2) in the face index space of dimension d (extent BS + 1 along d, BS elsewhere); written with
+// compile-time divisors per d (a runtime divisor costs ~20 instructions per division)
+template <int ND, int BS>
+__device__ __forceinline__ void face_decode(int it, int d, int (&cc)[3]) {
+  if (d == 0) {
+    cc[0] = it % (BS + 1); cc[1] = (it / (BS + 1)) % BS; cc[2] = ND == 3 ? it / ((BS + 1) * BS) : 0;
+  } else if (d == 1) {
+    cc[0] = it % BS; cc[1] = (it / BS) % (BS + 1); cc[2] = ND == 3 ? it / (BS * (BS + 1)) : 0;
+  } else {
+    cc[0] = it % BS; cc[1] = (it / BS) % BS; cc[2] = it / (BS * BS);
+  }
+}
+
 template <int ND, int BS, bool P2, int FLUX>
 __global__ void __launch_bounds__(RegCfg<ND, BS>::NT, (ND == 3 && BS == 8) ? 3 : 1)
 k_reg_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
@@ -551,8 +564,9 @@ k_reg_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
     (void)n0; (void)n1;
     // ---- (1) every face normal to d once: owner o = cell (c_d - 1), neighbour n = cell c_d
     for (int it = tid; it < NFD; it += NT) {
-      int c0 = it % m0, c1 = (it / m0) % m1, c2 = ND == 3 ? it / (m0 * m1) : 0;
-      int so = (c0 + 2) + PAD * ((c1 + 2) + (ND == 3 ? PAD * (c2 + 2) : 0)) - ss;  // owner sits one step below along d
+      int cc[3];
+      face_decode<ND, BS>(it, d, cc);
+      int so = (cc[0] + 2) + PAD * ((cc[1] + 2) + (ND == 3 ? PAD * (cc[2] + 2) : 0)) - ss;  // owner sits one step below along d
       int sn = so + ss;
       float po[NV], pn[NV], g0[NV], g1[NV], pl[NV], pr[NV];
 #pragma unroll
@@ -745,6 +759,79 @@ __device__ __forceinline__ void hyb_halo_grad(const float* __restrict__ sP, cons
   }
 }
 
+// ---- compact general path: the neighbours of a cell on one side as a short slot list, one gradient routine
+struct NL {
+  int cnt;
+  int s[4];
+  float h;
+};
+
+template <int ND, int BS, bool FINER>
+__device__ __forceinline__ NL nl_own(const FaceInfo& F, const int (&ii)[3], int l, int d, int side, int ss, float hd) {
+  NL r;
+  r.cnt = 1;
+  r.h = hd;
+  r.s[1] = r.s[2] = r.s[3] = 0;
+  bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+  if (inner || F.kind == 1) {
+    r.s[0] = side ? l + ss : l - ss;
+  } else if (F.kind == 0) {
+    r.s[0] = l;                       // box face: owner == neighbour == this cell
+  } else if (!FINER || F.kind == 2) {
+    int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
+    r.s[0] = F.base + (a2 >> 1) * F.n1 + (a1 >> 1);
+    r.h = F.hn;
+  } else {
+    int slot[4];
+    r.cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
+    for (int q = 0; q < r.cnt; ++q) r.s[q] = F.base + slot[q];
+    r.h = F.hn;
+  }
+  return r;
+}
+
+// near side of halo cell r (layer 0) of face (d, side): the own cells facing it
+template <int ND, int BS, bool FINER>
+__device__ __forceinline__ NL nl_halo_near(const FaceInfo& F, int side, int r, int d, float hd) {
+  NL o;
+  o.h = hd;
+  o.s[1] = o.s[2] = o.s[3] = 0;
+  int j1 = r % F.n1, j2 = r / F.n1;
+  int bnd = side ? BS - 1 : 0;
+  if (FINER && F.kind == 3) {
+    o.cnt = 1;
+    o.s[0] = pslot_c<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
+  } else {
+    o.cnt = ND == 3 ? 4 : 2;
+    for (int q = 0; q < o.cnt; ++q) o.s[q] = pslot_c<ND, BS>(d, bnd, 2 * j1 + (q & 1), 2 * j2 + (q >> 1));
+  }
+  return o;
+}
+
+// Green-Gauss gradient along one dimension of the NV staged variables at slot c (spacing hc), given the slot lists
+// of its low and high sides; weights 1/len, products first, sum in list order (src/accumulator.jl:95-106)
+template <int NV, int NS>
+__device__ __noinline__ void grad_lists(const float* __restrict__ sP, int c, float hc, NL lo, NL hi, int p2, float* __restrict__ g) {
+  float m[2][NV];
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const NL& L = side ? hi : lo;
+    const float w = 1.0f / (float)L.cnt;
+    const bool fast = p2 && L.h == hc;
+    for (int q = 0; q < L.cnt; ++q) {
+      const int n = L.s[q];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float fv = face_interp_f(sP[v * NS + c], sP[v * NS + n], hc, L.h, fast);
+        m[side][v] = q == 0 ? fv * w : m[side][v] + fv * w;
+      }
+    }
+  }
+  const float inv = 1.0f / hc;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) g[v] = p2 ? (m[1][v] - m[0][v]) * inv : (m[1][v] - m[0][v]) / hc;
+}
+
 template <int ND, int BS, bool FINER, bool P2, int FLUX>
 __global__ void __launch_bounds__(HybCfg<ND, BS, FINER>::NT, (ND == 3 && BS == 8 && !FINER) ? 3 : 1)
 k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
@@ -823,7 +910,7 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
       if (it < NFD + nlo + nhi) {
         int cc[3];
         if (it < NFD) {
-          cc[0] = it % m0; cc[1] = (it / m0) % m1; cc[2] = ND == 3 ? it / (m0 * m1) : 0;
+          face_decode<ND, BS>(it, d, cc);
         } else {
           int k = it - NFD;
           int cdv;
@@ -852,63 +939,46 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
             pn[v] = un;
           }
           Do = sD[so]; Dn = sD[sn];
-        } else if (cd >= 1 && cd <= BS - 1) {
-          // internal face next to an irregular block face: both cells are own cells, general gradients
-          int io[3] = {cc[0], cc[1], cc[2]};
-          io[d] -= 1;
-          hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, io, d, ss, hd, p2, inv_hd, g0);
-          hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, cc, d, ss, hd, p2, inv_hd, g1);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + so]; pn[v] = sP[v * NS + sn]; }
-          Do = sD[so]; Dn = sD[sn];
         } else {
-          // block face: cd == 0 (low) or cd == BS (high)
-          const int side = cd == 0 ? 0 : 1;
-          const FaceInfo& F = side ? FH : FL;
-          if (FINER && F.kind == 3) continue;  // its 2^(ND-1) fine faces per cell are the extra items below
-          int io[3] = {cc[0], cc[1], cc[2]};
-          io[d] = side ? BS - 1 : 0;
-          const int own = pslot<ND, BS>(io);
-          float gown[NV], ghal[NV], pown[NV], phal[NV];
-          hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, io, d, ss, hd, p2, inv_hd, gown);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) pown[v] = sP[v * NS + own];
-          float Down = sD[own], Dhal, hh;
-          if (F.kind == 0) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) { phal[v] = pown[v]; ghal[v] = gown[v]; }
-            Dhal = Down; hh = hd;
-          } else if (F.kind == 1) {  // same-level neighbour on this side, irregular face on the other side of the dim
-            int ih[3] = {cc[0], cc[1], cc[2]};
-            ih[d] = side ? BS : -1;
-            const int hs = pslot<ND, BS>(ih);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-              float u0 = sP[v * NS + hs], u1 = sP[v * NS + (side ? hs + ss : hs - ss)];
-              float fnear = face_interp_f(u0, pown[v], hd, hd, p2), ffar = face_interp_f(u0, u1, hd, hd, p2);
-              float df = side ? ffar - fnear : fnear - ffar;
-              ghal[v] = p2 ? df * inv_hd : df / hd;
-              phal[v] = u0;
+          // general item: describe owner and neighbour as (slot, spacing, low list, high list), one gradient routine
+          int co, cn;
+          float hco = hd, hcn = hd;
+          NL lo_o, hi_o, lo_n, hi_n;
+          if (cd >= 1 && cd <= BS - 1) {        // internal face next to an irregular block face: two own cells
+            int io[3] = {cc[0], cc[1], cc[2]};
+            io[d] -= 1;
+            co = so; cn = sn;
+            lo_o = nl_own<ND, BS, FINER>(FL, io, co, d, 0, ss, hd); hi_o = nl_own<ND, BS, FINER>(FH, io, co, d, 1, ss, hd);
+            lo_n = nl_own<ND, BS, FINER>(FL, cc, cn, d, 0, ss, hd); hi_n = nl_own<ND, BS, FINER>(FH, cc, cn, d, 1, ss, hd);
+          } else {                              // block face: cd == 0 (low) or cd == BS (high)
+            const int side = cd == 0 ? 0 : 1;
+            const FaceInfo& F = side ? FH : FL;
+            if (FINER && F.kind == 3) continue;  // its fine faces are the extra items below
+            int io[3] = {cc[0], cc[1], cc[2]};
+            io[d] = side ? BS - 1 : 0;
+            const int own = pslot<ND, BS>(io);
+            NL lo_w = nl_own<ND, BS, FINER>(FL, io, own, d, 0, ss, hd), hi_w = nl_own<ND, BS, FINER>(FH, io, own, d, 1, ss, hd);
+            int ch = own;
+            float hh = hd;
+            NL lo_h = lo_w, hi_h = hi_w;         // box face: both sides are the own cell
+            if (F.kind == 2) {                   // coarser neighbour
+              int a1 = cc[T1(d)], a2 = ND == 3 ? cc[T2(d)] : 0;
+              int hr = (a2 >> 1) * F.n1 + (a1 >> 1);
+              ch = F.base + hr;
+              hh = F.hn;
+              NL nearl = nl_halo_near<ND, BS, FINER>(F, side, hr, d, hd);
+              NL farl; farl.cnt = 1; farl.s[0] = ch + F.n1 * F.n2; farl.s[1] = farl.s[2] = farl.s[3] = 0; farl.h = hh;
+              lo_h = side ? nearl : farl;
+              hi_h = side ? farl : nearl;
             }
-            Dhal = sD[hs]; hh = hd;
-          } else {                   // coarser neighbour
-            int a1 = cc[T1(d)], a2 = ND == 3 ? cc[T2(d)] : 0;
-            int hr = (a2 >> 1) * F.n1 + (a1 >> 1);
-            const int hs = F.base + hr;
-            hyb_halo_grad<ND, BS, FINER, NV, NS>(sP, F, side, hr, d, hd, p2, ghal);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) phal[v] = sP[v * NS + hs];
-            Dhal = sD[hs]; hh = F.hn;
+            if (side) { co = own; hco = hd; lo_o = lo_w; hi_o = hi_w; cn = ch; hcn = hh; lo_n = lo_h; hi_n = hi_h; }
+            else      { co = ch; hco = hh; lo_o = lo_h; hi_o = hi_h; cn = own; hcn = hd; lo_n = lo_w; hi_n = hi_w; }
           }
-          if (side) {
+          grad_lists<NV, NS>(sP, co, hco, lo_o, hi_o, p2, g0);
+          grad_lists<NV, NS>(sP, cn, hcn, lo_n, hi_n, p2, g1);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) { po[v] = pown[v]; g0[v] = gown[v]; pn[v] = phal[v]; g1[v] = ghal[v]; }
-            Do = Down; Dn = Dhal; ho = hd; hn = hh;
-          } else {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) { po[v] = phal[v]; g0[v] = ghal[v]; pn[v] = pown[v]; g1[v] = gown[v]; }
-            Do = Dhal; Dn = Down; ho = hh; hn = hd;
-          }
+          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + co]; pn[v] = sP[v * NS + cn]; }
+          Do = sD[co]; Dn = sD[cn]; ho = hco; hn = hcn;
         }
       } else {
         // fine face k of a finer neighbour: halo fine cell k <-> own coarse cell (j1/2, j2/2)
@@ -922,18 +992,23 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
         io[T1(d)] = j1 >> 1;
         if (ND == 3) io[T2(d)] = j2 >> 1;
         const int own = pslot<ND, BS>(io), hs = F.base + k;
-        float gown[NV], ghal[NV];
-        hyb_own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, io, d, ss, hd, p2, inv_hd, gown);
-        hyb_halo_grad<ND, BS, FINER, NV, NS>(sP, F, side, k, d, hd, p2, ghal);
+        NL lo_w = nl_own<ND, BS, FINER>(FL, io, own, d, 0, ss, hd), hi_w = nl_own<ND, BS, FINER>(FH, io, own, d, 1, ss, hd);
+        NL nearl = nl_halo_near<ND, BS, FINER>(F, side, k, d, hd);
+        NL farl; farl.cnt = 1; farl.s[0] = hs + F.n1 * F.n2; farl.s[1] = farl.s[2] = farl.s[3] = 0; farl.h = F.hn;
+        int co, cn;
+        float hco, hcn;
         if (side) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + own]; g0[v] = gown[v]; pn[v] = sP[v * NS + hs]; g1[v] = ghal[v]; }
-          Do = sD[own]; Dn = sD[hs]; ho = hd; hn = F.hn;
+          co = own; hco = hd; cn = hs; hcn = F.hn;
+          grad_lists<NV, NS>(sP, co, hco, lo_w, hi_w, p2, g0);
+          grad_lists<NV, NS>(sP, cn, hcn, nearl, farl, p2, g1);
         } else {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + hs]; g0[v] = ghal[v]; pn[v] = sP[v * NS + own]; g1[v] = gown[v]; }
-          Do = sD[hs]; Dn = sD[own]; ho = F.hn; hn = hd;
+          co = hs; hco = F.hn; cn = own; hcn = hd;
+          grad_lists<NV, NS>(sP, co, hco, farl, nearl, p2, g0);
+          grad_lists<NV, NS>(sP, cn, hcn, lo_w, hi_w, p2, g1);
         }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + co]; pn[v] = sP[v * NS + cn]; }
+        Do = sD[co]; Dn = sD[cn]; ho = hco; hn = hcn;
         fslot = NFD + side * (C::NX / 2) + k;
       }
       float pl[NV], pr[NV];
