@@ -26,6 +26,8 @@ struct ibx_ctx {
   // scratch for fused kernels (ghost staging etc.)
   float* d_scratch = nullptr;
   int64_t scratch_cap = 0;
+  float* d_scratch2 = nullptr;  // fluxes of the general faces of irregular blocks (two-pass hybrid kernel)
+  int64_t scratch2_cap = 0;
   // end-to-end staging arrays
   ibx_array e2e_Q = 0, e2e_R = 0, e2e_cfl = 0;
   // NCCL

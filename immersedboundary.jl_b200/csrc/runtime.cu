@@ -105,6 +105,7 @@ int ibx_finalize(ibx_ctx* c) {
   if (c->d_red) cudaFree(c->d_red);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_scratch2) cudaFree(c->d_scratch2);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);

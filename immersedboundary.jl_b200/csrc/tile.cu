@@ -832,15 +832,20 @@ __device__ __noinline__ void grad_lists(const float* __restrict__ sP, int c, flo
   for (int v = 0; v < NV; ++v) g[v] = p2 ? (m[1][v] - m[0][v]) * inv : (m[1][v] - m[0][v]) / hc;
 }
 
-template <int ND, int BS, bool FINER, bool P2, int FLUX>
+// MODE 0: everything in one kernel.  MODE 1: only the general faces, fluxes written to a global scratch (GF, GC).
+// MODE 2: the uniform faces (lean loop), general fluxes read back from the scratch, divergence.  Splitting keeps
+// each kernel's working set of instructions near the 32 KB instruction cache (ncu: 32 % of the samples of the
+// one-kernel form were instruction-fetch stalls).
+template <int ND, int BS, bool FINER, bool P2, int FLUX, int MODE>
 __global__ void __launch_bounds__(HybCfg<ND, BS, FINER>::NT, (ND == 3 && BS == 8 && !FINER) ? 3 : 1)
 k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
            ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, float* __restrict__ R,
-           float* __restrict__ cfl) {
+           float* __restrict__ cfl, double* __restrict__ GF, float* __restrict__ GC) {
   using C = HybCfg<ND, BS, FINER>;
   using RC = RegCfg<ND, BS>;
   constexpr int NV = C::NV, PAD = RC::PAD, TS = RC::TS, CPB = RC::CPB, NT = C::NT, NFD = RC::NFD, FACE = RC::FACE;
   constexpr int NS = C::NSLOT, NFS = C::NFS, MAXL = C::MAXL;
+  constexpr int NSL = 4 * FACE + C::NX;  // scratch slots per (block, dimension): 2 x 2 x FACE general faces + fine faces
   extern __shared__ double smem_d[];
   __shared__ FaceInfo fi[2 * ND];
   double* sF = smem_d;                  // [NV][NFS]
@@ -866,6 +871,7 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
   for (int f = 0; f < 2 * ND; ++f) {
     const FaceInfo& F = fi[f];
     if (F.kind == 0) continue;
+    if (MODE == 2 && F.kind != 1) continue;  // coarser / finer halos are only read by the general faces
     int d = f >> 1, side = f & 1, n1n2 = F.n1 * F.n2;
     for (int k = tid; k < 2 * n1n2; k += NT) {
       int layer = k / n1n2, r = k - layer * n1n2;
@@ -903,10 +909,11 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
     //      [low block face, first internal face] if the low face is irregular, [last internal face, high block face]
     //      if the high one is, then the fine faces of finer neighbours.
     const int nlo = irr_lo ? 2 * FACE : 0, nhi = irr_hi ? 2 * FACE : 0;
-    for (int it = tid; it < NFD + nlo + nhi + nxl + nxh; it += NT) {
+    const int64_t gbase = ((int64_t)blockIdx.x * ND + d) * NSL;
+    for (int it = (MODE == 1 ? NFD + tid : tid); it < (MODE == 2 ? NFD : NFD + nlo + nhi + nxl + nxh); it += NT) {
       float po[NV], pn[NV], g0[NV], g1[NV];
       float ho = hd, hn = hd, Do, Dn;
-      int fslot = it;
+      int fslot = it, sid = 0;
       if (it < NFD + nlo + nhi) {
         int cc[3];
         if (it < NFD) {
@@ -914,8 +921,8 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
         } else {
           int k = it - NFD;
           int cdv;
-          if (k < nlo) cdv = k / FACE;                     // 0: low block face, 1: first internal face
-          else { k -= nlo; cdv = BS - 1 + k / FACE; }      // BS-1: last internal face, BS: high block face
+          if (k < nlo) { cdv = k / FACE; sid = k; }                           // 0: low block face, 1: first internal face
+          else { k -= nlo; cdv = BS - 1 + k / FACE; sid = 2 * FACE + k; }     // BS-1: last internal face, BS: high block face
           int pq = k % FACE;
           cc[0] = cc[1] = cc[2] = 0;
           cc[d] = cdv;
@@ -1010,6 +1017,7 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
         for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + co]; pn[v] = sP[v * NS + cn]; }
         Do = sD[co]; Dn = sD[cn]; ho = hco; hn = hcn;
         fslot = NFD + side * (C::NX / 2) + k;
+        sid = 4 * FACE + side * (C::NX / 2) + k;
       }
       float pl[NV], pr[NV];
       double F_[NV];
@@ -1025,9 +1033,42 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
       }
       float ao = sqrtf(gr * clampT(po[1])), an = sqrtf(gr * clampT(pn[1]));
       float ct = fabsf(face_interp_f(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), ho, hn, fast)) + face_interp_f(ao, an, ho, hn, fast);
+      if (MODE == 1) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) sF[v * NFS + fslot] = F_[v];
-      sC[fslot] = ct;
+        for (int v = 0; v < NV; ++v) GF[(gbase + sid) * NV + v] = F_[v];
+        GC[gbase + sid] = ct;
+      } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sF[v * NFS + fslot] = F_[v];
+        sC[fslot] = ct;
+      }
+    }
+    if (MODE == 1) continue;  // general-only pass: no divergence here
+    if (MODE == 2) {
+      // fetch the fluxes of the general faces computed by the MODE 1 pass (same enumeration, same slots)
+      for (int k = tid; k < nlo + nhi + nxl + nxh; k += NT) {
+        int fslot, sid;
+        if (k < nlo + nhi) {
+          int kk = k, cdv;
+          if (kk < nlo) { cdv = kk / FACE; sid = kk; }
+          else { kk -= nlo; cdv = BS - 1 + kk / FACE; sid = 2 * FACE + kk; }
+          if (FINER && ((cdv == 0 && FL.kind == 3) || (cdv == BS && FH.kind == 3))) continue;  // replaced by fine faces
+          int pq = kk % FACE, cc[3] = {0, 0, 0};
+          cc[d] = cdv;
+          cc[T1(d)] = pq % BS;
+          if (ND == 3) cc[T2(d)] = pq / BS;
+          fslot = cc[0] + m0 * (cc[1] + (ND == 3 ? m1 * cc[2] : 0));
+        } else {
+          int kx = k - nlo - nhi;
+          int side = kx >= nxl ? 1 : 0;
+          int kf = kx - (side ? nxl : 0);
+          fslot = NFD + side * (C::NX / 2) + kf;
+          sid = 4 * FACE + side * (C::NX / 2) + kf;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) sF[v * NFS + fslot] = GF[(gbase + sid) * NV + v];
+        sC[fslot] = GC[gbase + sid];
+      }
     }
     __syncthreads();
     // ---- (2) divergence
@@ -1085,6 +1126,7 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
     }
     __syncthreads();
   }
+  if (MODE == 1) return;
 #pragma unroll
   for (int q = 0; q < RC::CPT; ++q) {
     int l = tid + q * NT;
@@ -1096,25 +1138,52 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
   }
 }
 
+template <int ND, int BS, bool FINER, bool P2, int FLUX, int MODE>
+int launch_hyb_mode(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
+                    float* R, float* cfl, double* GF, float* GC) {
+  using C = HybCfg<ND, BS, FINER>;
+  static bool attr = false;
+  if (!attr) {
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr = true;
+  }
+  k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
+
+template <int ND, int BS, bool FINER, bool P2, int FLUX>
+int launch_hyb_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
+                    float* R, float* cfl) {
+  using C = HybCfg<ND, BS, FINER>;
+  // blocks with a finer neighbour: few, heavy (1 CTA/SM either way) -- measured faster in one pass
+  if (FINER || getenv("IBX_HYB_ONEPASS") != nullptr)
+    return launch_hyb_mode<ND, BS, FINER, P2, FLUX, 0>(c, D, blocks, n, f, P, S, R, cfl, nullptr, nullptr);
+  // two passes through a global scratch holding the fluxes of the general faces
+  constexpr int64_t NSL = 4 * C::FACE + C::NX;
+  int64_t slots = (int64_t)n * ND * NSL;
+  int64_t need = slots * (C::NV * 2 + 1);  // floats: NV doubles + 1 float per slot
+  if (need > c->scratch2_cap) {
+    if (c->d_scratch2) cudaFree(c->d_scratch2);
+    c->d_scratch2 = nullptr;
+    c->scratch2_cap = 0;
+    CU(cudaMalloc((void**)&c->d_scratch2, (size_t)need * sizeof(float)));
+    c->scratch2_cap = need;
+  }
+  double* GF = (double*)c->d_scratch2;
+  float* GC = (float*)(GF + slots * C::NV);
+  int rc;
+  if ((rc = launch_hyb_mode<ND, BS, FINER, P2, FLUX, 1>(c, D, blocks, n, f, P, S, R, cfl, GF, GC))) return rc;
+  return launch_hyb_mode<ND, BS, FINER, P2, FLUX, 2>(c, D, blocks, n, f, P, S, R, cfl, GF, GC);
+}
+
 template <int ND, int BS, bool FINER, bool P2>
 int launch_hyb(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, int flux_kind, const float* P,
                const float* S, float* R, float* cfl) {
-  using C = HybCfg<ND, BS, FINER>;
   if (n == 0) return IBX_OK;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr = true;
-  }
-  if (flux_kind == 0)
-    k_hyb_flux<ND, BS, FINER, P2, 0><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
-  else
-    k_hyb_flux<ND, BS, FINER, P2, 1><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
-  LAUNCH_CHECK();
-  return IBX_OK;
+  if (flux_kind == 0) return launch_hyb_flux<ND, BS, FINER, P2, 0>(c, D, blocks, n, f, P, S, R, cfl);
+  return launch_hyb_flux<ND, BS, FINER, P2, 1>(c, D, blocks, n, f, P, S, R, cfl);
 }
 
 // lean sensor kernel for regular blocks: padded (BS+2)^ND tile of p, uniform loop (same bits as k_tile_sensor)
