@@ -42,6 +42,10 @@ ibx_domain* find_domain(const ibx_domain* d);
 ibx_accum* find_accum(const ibx_accum* a);
 bool get_array(ibx_ctx* c, ibx_array h, ibx_ctx::Arr& out);
 float* ensure_scratch(ibx_ctx* c, int64_t nfloats);
+// pencil-marching flux pass (march.cu)
+bool march_supported(const ibx_domain& D);
+int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,
+               const float* S, float* R, float* cfl, const double* GF, const float* GC);
 
 #define CU(call)                                                                      \
   do {                                                                                \

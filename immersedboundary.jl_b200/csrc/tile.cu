@@ -15,6 +15,7 @@
 // Work per dimension: gradients -> face fluxes (each face ONCE: MUSCL + HLL) -> divergence; three barriers.
 #include "device.cuh"
 #include "physics.cuh"
+#include "tile_common.cuh"
 
 using namespace ibx;
 using namespace ibxk;
@@ -37,85 +38,6 @@ struct Cfg {
   static constexpr size_t SMEM_SENSOR = sizeof(float) * ((size_t)CPB + NFACES * MAXL1);
 };
 
-struct FaceInfo {
-  int kind, n1, n2, base, nfaces;
-  float hn;
-  int nb[4];
-  int sub1, sub2;
-};
-
-__device__ __forceinline__ int T1(int d) { return d == 0 ? 1 : 0; }
-__device__ __forceinline__ int T2(int d) { return d == 2 ? 1 : 2; }
-
-template <int ND, int BS>
-__device__ __forceinline__ int compose(int d, int cn, int c1, int c2) {
-  int idx[3] = {0, 0, 0};
-  idx[d] = cn;
-  idx[T1(d)] = c1;
-  if (ND == 3) idx[T2(d)] = c2;
-  return idx[0] + BS * (idx[1] + BS * idx[2]);
-}
-
-template <int ND, int BS>
-__device__ __forceinline__ void split(int l, int (&ii)[3]) {
-  ii[0] = l % BS;
-  ii[1] = (l / BS) % BS;
-  ii[2] = ND == 3 ? l / (BS * BS) : 0;
-}
-
-// base: first slot of this face's halo area; layers: 1 (sensor) or 2 (flux)
-template <int ND, int BS>
-__device__ __forceinline__ void fill_face_info(FaceInfo& fi, const BlockFace& bf, int base, float h) {
-  fi.kind = bf.kind >= 1 && bf.kind <= 3 ? bf.kind : 0;
-  fi.sub1 = bf.sub[0];
-  fi.sub2 = bf.sub[1];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) fi.nb[q] = bf.nb[q];
-  int n = fi.kind == 1 ? BS : (fi.kind == 2 ? BS / 2 : (fi.kind == 3 ? 2 * BS : 0));
-  fi.n1 = n;
-  fi.n2 = ND == 3 ? n : (n ? 1 : 0);
-  fi.hn = fi.kind == 2 ? h * 2.0f : (fi.kind == 3 ? h * 0.5f : h);
-  fi.base = base;
-  fi.nfaces = fi.kind == 3 ? fi.n1 * fi.n2 : (ND == 3 ? BS * BS : BS);
-}
-
-// global cell id of halo cell (j1, j2, layer) of face (d, side)
-template <int ND, int BS>
-__device__ __forceinline__ int64_t halo_cell(const FaceInfo& fi, int d, int side, int j1, int j2, int layer, int64_t cpb) {
-  int jn = side ? layer : BS - 1 - layer;
-  int64_t nb;
-  int J1 = j1, J2 = j2;
-  if (fi.kind == 1) {
-    nb = fi.nb[0];
-  } else if (fi.kind == 2) {
-    nb = fi.nb[0];
-    J1 = j1 + fi.sub1 * (BS / 2);
-    J2 = ND == 3 ? j2 + fi.sub2 * (BS / 2) : 0;
-  } else {
-    int q1 = j1 / BS, q2 = ND == 3 ? j2 / BS : 0;
-    nb = fi.nb[q1 + 2 * q2];
-    J1 = j1 % BS;
-    J2 = ND == 3 ? j2 % BS : 0;
-  }
-  return nb * cpb + compose<ND, BS>(d, jn, J1, J2);
-}
-
-// layer-0 halo slots (relative to fi.base) of the cells facing own cell (a1, a2); ascending cell id
-template <int ND, int BS>
-__device__ __forceinline__ int own_to_halo(const FaceInfo& fi, int a1, int a2, int (&slot)[4]) {
-  if (fi.kind == 1) {
-    slot[0] = a2 * fi.n1 + a1;
-    return 1;
-  }
-  if (fi.kind == 2) {
-    slot[0] = (a2 >> 1) * fi.n1 + (a1 >> 1);
-    return 1;
-  }
-  constexpr int CNT = ND == 3 ? 4 : 2;
-#pragma unroll
-  for (int q = 0; q < CNT; ++q) slot[q] = (ND == 3 ? (2 * a2 + (q >> 1)) * fi.n1 : 0) + 2 * a1 + (q & 1);
-  return CNT;
-}
 
 // ------------------------------------------------------------------------------------------ sensor pass
 // D = JST_sensor(part, p) with dim = 0 (src/ImmersedBoundary.jl:1077-1097) for the cells of one block
@@ -1281,6 +1203,42 @@ int launch_pair(ibx_ctx* c, const ibx_domain& D, const int32_t* sens_blocks, int
   return IBX_OK;
 }
 
+// general-face pass of the irregular blocks (MODE 1) followed by the marching kernel on all owned blocks
+template <int ND, int BS>
+int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* P, const float* S, float* R, float* cfl) {
+  using CP = HybCfg<ND, BS, false>;
+  using CF = HybCfg<ND, BS, true>;
+  constexpr int NV = CP::NV;
+  int rc;
+  if ((rc = march_flux(c, D, D.d_blk_own_regular, D.n_own_regular, 0, f, flux_kind, P, S, R, cfl, nullptr, nullptr))) return rc;
+  const int64_t sl_p = (int64_t)D.n_own_plain * ND * (4 * CP::FACE + CP::NX), sl_f = (int64_t)D.n_own_finer * ND * (4 * CF::FACE + CF::NX);
+  if (sl_p + sl_f == 0) return IBX_OK;
+  const int64_t need = (sl_p + sl_f) * (NV * 2 + 1);  // floats: NV doubles + 1 float per slot
+  if (need > c->scratch2_cap) {
+    if (c->d_scratch2) cudaFree(c->d_scratch2);
+    c->d_scratch2 = nullptr;
+    c->scratch2_cap = 0;
+    CU(cudaMalloc((void**)&c->d_scratch2, (size_t)need * sizeof(float)));
+    c->scratch2_cap = need;
+  }
+  double* GFp = (double*)c->d_scratch2;
+  double* GFf = GFp + sl_p * NV;
+  float* GCp = (float*)(GFf + sl_f * NV);
+  float* GCf = GCp + sl_p;
+  if (D.n_own_plain) {
+    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, false, true, 0, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp);
+    else rc = launch_hyb_mode<ND, BS, false, true, 1, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp);
+    if (rc) return rc;
+  }
+  if (D.n_own_finer) {
+    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, true, true, 0, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf);
+    else rc = launch_hyb_mode<ND, BS, true, true, 1, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf);
+    if (rc) return rc;
+  }
+  if ((rc = march_flux(c, D, D.d_blk_own_plain, D.n_own_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp))) return rc;
+  return march_flux(c, D, D.d_blk_own_finer, D.n_own_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf);
+}
+
 template <int ND, int BS>
 int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S, float* R, float* cfl) {
   int64_t N = D.ncells;
@@ -1296,6 +1254,11 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   }
   if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
   if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+  // 3-D 8^3 blocks with power-of-two spacings: pencil-marching kernel (march.cu) on every owned block; the general
+  // faces of the irregular blocks are computed first (MODE 1) and handed over through a global scratch
+  if constexpr (ND == 3 && BS == 8) {
+    if (march_supported(D) && getenv("IBX_NO_MARCH") == nullptr) return run_march<ND, BS>(c, D, f, flux_kind, P, S, R, cfl);
+  }
   // fluxes: regular blocks (all neighbours same level) through the lean kernel, the rest through the general one
   if ((rc = D.all_pow2 ? launch_reg<ND, BS, true>(c, D, f, flux_kind, P, S, R, cfl) : launch_reg<ND, BS, false>(c, D, f, flux_kind, P, S, R, cfl))) return rc;
   // IBX_TILE_GENERAL=1 routes the irregular blocks through the older general tile kernel (cross-check)
