@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
                 if rc != 0:
                     raise RuntimeError(f"nvcc failed on {src}")
     objs = [os.path.join(OBJ, s + ".o") for s in _sources()]
-    if jobs or not os.path.exists(LIB) or force:
+    if jobs or not os.path.exists(LIB) or force or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -110,6 +110,22 @@ def euler_step_host(dom, fluid, bcs, Q_host, R_host, cfl_host, flux="hll"):
          ptr(Q_host), ptr(R_host), ptr(cfl_host))
 
 
+def euler_step_host_begin(dom, fluid, bcs, Q_host, R_host, cfl_host, slot, flux="hll"):
+    """Asynchronous half of ``euler_step_host``: enqueue H2D(Q) -> ghost updates -> residual -> D2H(R, cfl) on
+    ``slot`` (0 or 1) and return.  Independent evaluations on alternating slots overlap their copies (full-duplex
+    PCIe) and compute; the host buffers must stay alive until ``euler_step_host_end(slot)``."""
+    dom.upload()
+    specs = (_lib.BCSpec * max(len(bcs), 1))(*[bc.spec(dom.boundary_index[name]) for name, bc in bcs])
+    assert Q_host.flags.f_contiguous and R_host.flags.f_contiguous and Q_host.dtype == np.float32
+    call("ibx_euler_step_host_begin", context(), dom._h, fluid.c, 0 if flux == "hll" else 1, len(bcs), specs,
+         ptr(Q_host), ptr(R_host), ptr(cfl_host), int(slot))
+
+
+def euler_step_host_end(slot):
+    """Block until the evaluation enqueued on ``slot`` has delivered R and cfl to its host buffers."""
+    call("ibx_euler_step_host_end", context(), int(slot))
+
+
 def pinned_empty(shape, order="F"):
     """float32 array backed by pinned host memory (``ibx_host_alloc``) for the end-to-end path."""
     n = int(np.prod(shape))

@@ -29,7 +29,13 @@ struct ibx_ctx {
   float* d_scratch2 = nullptr;  // fluxes of the general faces of irregular blocks (two-pass hybrid kernel)
   int64_t scratch2_cap = 0;
   // end-to-end staging arrays
-  ibx_array e2e_Q = 0, e2e_R = 0, e2e_cfl = 0;
+  // two slots: the copies of one call overlap the compute / opposite-direction copies of the other (PCIe is full duplex)
+  struct E2ESlot {
+    ibx_array Q = 0, R = 0, cfl = 0;
+    cudaEvent_t up = nullptr, done = nullptr, down = nullptr;
+    bool busy = false;
+  } e2e[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // NCCL
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;

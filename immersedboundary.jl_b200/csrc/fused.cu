@@ -584,39 +584,80 @@ int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, 
   return IBX_OK;
 }
 
-int ibx_euler_step_host(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
-                        const float* Q_host, float* R_host, float* cfl_host) {
+static int e2e_slot_prepare(ibx_ctx* c, ibx_ctx::E2ESlot& S, int64_t N, int nv) {
+  int rc;
+  if (!c->h2d_stream) {
+    CU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  }
+  if (!S.up) {
+    CU(cudaEventCreateWithFlags(&S.up, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&S.down, cudaEventDisableTiming));
+  }
+  if (S.Q) {
+    ibx_ctx::Arr probe;
+    if (get_array(c, S.Q, probe) && (probe.rows != N || probe.cols != nv)) {
+      ibx_array_free(c, S.Q);
+      ibx_array_free(c, S.R);
+      ibx_array_free(c, S.cfl);
+      S.Q = 0;
+    }
+  }
+  if (!S.Q) {
+    if ((rc = ibx_array_alloc(c, N, nv, &S.Q))) return rc;
+    if ((rc = ibx_array_alloc(c, N, nv, &S.R))) return rc;
+    if ((rc = ibx_array_alloc(c, N, 1, &S.cfl))) return rc;
+  }
+  return IBX_OK;
+}
+
+int ibx_euler_step_host_begin(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                              const float* Q_host, float* R_host, float* cfl_host, int slot) {
   CHECK_CTX(c);
   GET_DOM(D, d);
+  if (slot < 0 || slot > 1) return fail(IBX_ERR_ARG, "ibx_euler_step_host_begin: slot must be 0 or 1");
+  ibx_ctx::E2ESlot& S = c->e2e[slot];
+  if (S.busy) return fail(IBX_ERR_STATE, "ibx_euler_step_host_begin: slot still in flight (call ibx_euler_step_host_end first)");
   int nv = D.nd + 2;
   int64_t N = D.ncells;
   int rc;
-  if (c->e2e_Q) {
-    ibx_ctx::Arr probe;
-    if (get_array(c, c->e2e_Q, probe) && (probe.rows != N || probe.cols != nv)) {
-      ibx_array_free(c, c->e2e_Q);
-      ibx_array_free(c, c->e2e_R);
-      ibx_array_free(c, c->e2e_cfl);
-      c->e2e_Q = 0;
-    }
-  }
-  if (!c->e2e_Q) {
-    if ((rc = ibx_array_alloc(c, N, nv, &c->e2e_Q))) return rc;
-    if ((rc = ibx_array_alloc(c, N, nv, &c->e2e_R))) return rc;
-    if ((rc = ibx_array_alloc(c, N, 1, &c->e2e_cfl))) return rc;
-  }
-  GET_ARR(Q, c->e2e_Q);
-  GET_ARR(R, c->e2e_R);
-  GET_ARR(CF, c->e2e_cfl);
-  if (Q.rows != N || Q.cols != nv) return fail(IBX_ERR_STATE, "ibx_euler_step_host: staging arrays belong to a different domain");
-  CU(cudaMemcpyAsync(Q.p, Q_host, (size_t)N * nv * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = e2e_slot_prepare(c, S, N, nv))) return rc;
+  GET_ARR(Q, S.Q);
+  GET_ARR(R, S.R);
+  GET_ARR(CF, S.cfl);
+  // H2D on its own stream -> compute stream -> D2H on its own stream, chained by events
+  CU(cudaMemcpyAsync(Q.p, Q_host, (size_t)N * nv * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+  CU(cudaEventRecord(S.up, c->h2d_stream));
+  CU(cudaStreamWaitEvent(c->stream, S.up, 0));
   for (int k = 0; k < nbc; ++k)
-    if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, c->e2e_Q))) return rc;
-  if ((rc = ibx_residual_euler(c, d, f, flux_kind, c->e2e_Q, c->e2e_R, c->e2e_cfl))) return rc;
-  CU(cudaMemcpyAsync(R_host, R.p, (size_t)N * nv * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(cfl_host, CF.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+    if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, S.Q))) return rc;
+  if ((rc = ibx_residual_euler(c, d, f, flux_kind, S.Q, S.R, S.cfl))) return rc;
+  CU(cudaEventRecord(S.done, c->stream));
+  CU(cudaStreamWaitEvent(c->d2h_stream, S.done, 0));
+  CU(cudaMemcpyAsync(R_host, R.p, (size_t)N * nv * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+  CU(cudaMemcpyAsync(cfl_host, CF.p, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+  CU(cudaEventRecord(S.down, c->d2h_stream));
+  S.busy = true;
   return IBX_OK;
+}
+
+int ibx_euler_step_host_end(ibx_ctx* c, int slot) {
+  CHECK_CTX(c);
+  if (slot < 0 || slot > 1) return fail(IBX_ERR_ARG, "ibx_euler_step_host_end: slot must be 0 or 1");
+  ibx_ctx::E2ESlot& S = c->e2e[slot];
+  if (!S.busy) return IBX_OK;
+  CU(cudaEventSynchronize(S.down));
+  S.busy = false;
+  return IBX_OK;
+}
+
+int ibx_euler_step_host(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                        const float* Q_host, float* R_host, float* cfl_host) {
+  int rc;
+  if ((rc = ibx_euler_step_host_end(c, 0))) return rc;
+  if ((rc = ibx_euler_step_host_begin(c, d, f, flux_kind, nbc, bcs, Q_host, R_host, cfl_host, 0))) return rc;
+  return ibx_euler_step_host_end(c, 0);
 }
 
 }  // extern "C"

@@ -108,6 +108,13 @@ int ibx_finalize(ibx_ctx* c) {
   if (c->d_scratch2) cudaFree(c->d_scratch2);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  for (auto& S : c->e2e) {
+    if (S.up) cudaEventDestroy(S.up);
+    if (S.done) cudaEventDestroy(S.done);
+    if (S.down) cudaEventDestroy(S.down);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);

@@ -41,7 +41,7 @@ struct Cfg {
 
 // ------------------------------------------------------------------------------------------ sensor pass
 // D = JST_sensor(part, p) with dim = 0 (src/ImmersedBoundary.jl:1077-1097) for the cells of one block
-template <int ND, int BS, bool FINER>
+template <int ND, int BS, bool FINER, bool P2 = false>
 __global__ void __launch_bounds__(Cfg<ND, BS, FINER>::NT)
 k_tile_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
               const float* __restrict__ p, float* __restrict__ D) {
@@ -63,9 +63,9 @@ k_tile_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ 
     for (int k = tid; k < n; k += C::NT) sp[F.base + k] = p[halo_cell<ND, BS>(F, d, side, k % F.n1, k / F.n1, 0, C::CPB)];
   }
   __syncthreads();
-  float h[ND];
+  float h[ND], ih[ND];
 #pragma unroll
-  for (int d = 0; d < ND; ++d) h[d] = bh[b * ND + d];
+  for (int d = 0; d < ND; ++d) { h[d] = bh[b * ND + d]; ih[d] = 1.0f / h[d]; }
   for (int l = tid; l < C::CPB; l += C::NT) {
     int ii[3];
     split<ND, BS>(l, ii);
@@ -99,7 +99,8 @@ k_tile_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ 
         g[side] = accg;
         a[side] = acca;
       }
-      float gg = (g[1] - g[0]) / h[d], ugg = (a[1] + a[0]) / h[d];
+      // P2: h is a power of two, x / h == x * (1 / h) bit for bit (physics.cuh)
+      float gg = P2 ? (g[1] - g[0]) * ih[d] : (g[1] - g[0]) / h[d], ugg = P2 ? (a[1] + a[0]) * ih[d] : (a[1] + a[0]) / h[d];
       nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ugg));
       stride *= BS;
     }
@@ -589,6 +590,7 @@ struct HybCfg {
   static constexpr int NFS = R::NFD + NX;
   static constexpr int NT = R::NT;
   static constexpr size_t SMEM = sizeof(double) * (size_t)NV * NFS + sizeof(float) * ((size_t)(NV + 1) * NSLOT + NFS);
+  static constexpr size_t SMEM_GENERAL = sizeof(float) * ((size_t)(NV + 1) * NSLOT);   // MODE 1: fluxes go to global memory
 };
 
 template <int ND, int BS>
@@ -770,30 +772,57 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
   constexpr int NSL = 4 * FACE + C::NX;  // scratch slots per (block, dimension): 2 x 2 x FACE general faces + fine faces
   extern __shared__ double smem_d[];
   __shared__ FaceInfo fi[2 * ND];
-  double* sF = smem_d;                  // [NV][NFS]
-  float* sP = (float*)(sF + NV * NFS);  // [NV][NS]
+  double* sF = smem_d;                  // [NV][NFS] (absent in MODE 1)
+  float* sP = (float*)(sF + (MODE == 1 ? 0 : NV * NFS));  // [NV][NS]
   float* sD = sP + NV * NS;             // [NS]
   float* sC = sD + NS;                  // [NFS]
   const int64_t b = blocks[blockIdx.x];
   const int tid = threadIdx.x;
   const int64_t cell0 = b * CPB;
   if (tid < 2 * ND) fill_face_info<ND, BS>(fi[tid], faces[b * (2 * ND) + tid], TS + tid * 2 * MAXL, bh[b * ND + (tid >> 1)]);
-  __syncthreads();
-  // ---- stage own cells into the padded tile
-  for (int l = tid; l < CPB; l += NT) {
-    int ii[3];
-    split<ND, BS>(l, ii);
-    int s = pslot<ND, BS>(ii);
+  // ---- stage own cells into the padded tile (float4 along x when a row has 4+ cells; all loads before the stores)
+  if constexpr (BS % 4 == 0) {
+    constexpr int NQ = (NV + 1) * CPB / 4, PERQ = (NQ + NT - 1) / NT;
+    float4 buf[PERQ];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) sP[v * NS + s] = P[(int64_t)v * N + cell0 + l];
-    sD[s] = Dg[cell0 + l];
+    for (int k = 0; k < PERQ; ++k) {
+      const int it = tid + k * NT;
+      if (it < NQ) {
+        const int v = it / (CPB / 4), l = 4 * (it - v * (CPB / 4));
+        buf[k] = *reinterpret_cast<const float4*>((v < NV ? P + (int64_t)v * N : Dg) + cell0 + l);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PERQ; ++k) {
+      const int it = tid + k * NT;
+      if (it < NQ) {
+        const int v = it / (CPB / 4), l = 4 * (it - v * (CPB / 4));
+        int ii[3];
+        split<ND, BS>(l, ii);
+        float* t = sP + v * NS + pslot<ND, BS>(ii);
+        t[0] = buf[k].x; t[1] = buf[k].y; t[2] = buf[k].z; t[3] = buf[k].w;
+      }
+    }
+  } else {
+    for (int l = tid; l < CPB; l += NT) {
+      int ii[3];
+      split<ND, BS>(l, ii);
+      int s = pslot<ND, BS>(ii);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) sP[v * NS + s] = P[(int64_t)v * N + cell0 + l];
+      sD[s] = Dg[cell0 + l];
+    }
   }
+  __syncthreads();
   // ---- halos: same-level faces into the padded slabs, coarser / finer faces into their own areas
 #pragma unroll 1
   for (int f = 0; f < 2 * ND; ++f) {
     const FaceInfo& F = fi[f];
     if (F.kind == 0) continue;
     if (MODE == 2 && F.kind != 1) continue;  // coarser / finer halos are only read by the general faces
+    // ... and, with 4 or more cells per block edge, the general faces (block face + first internal face: own cells
+    // 0..2 along d and the irregular halo) never read a same-level halo
+    if (MODE == 1 && F.kind == 1 && BS >= 4) continue;
     int d = f >> 1, side = f & 1, n1n2 = F.n1 * F.n2;
     for (int k = tid; k < 2 * n1n2; k += NT) {
       int layer = k / n1n2, r = k - layer * n1n2;
@@ -1065,12 +1094,13 @@ int launch_hyb_mode(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int 
                     float* R, float* cfl, double* GF, float* GC) {
   using C = HybCfg<ND, BS, FINER>;
   static bool attr = false;
+  constexpr size_t SM = MODE == 1 ? C::SMEM_GENERAL : C::SMEM;
   if (!attr) {
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM));
     CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE><<<n, C::NT, SM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
 }
@@ -1179,10 +1209,12 @@ int launch_pair(ibx_ctx* c, const ibx_domain& D, const int32_t* sens_blocks, int
     if (n_sens == 0) return IBX_OK;
     static bool attr = false;
     if (!attr && C::SMEM_SENSOR > 48 * 1024) {
-      CU(cudaFuncSetAttribute(k_tile_sensor<ND, BS, FINER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_SENSOR));
+      CU(cudaFuncSetAttribute(k_tile_sensor<ND, BS, FINER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_SENSOR));
+      CU(cudaFuncSetAttribute(k_tile_sensor<ND, BS, FINER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_SENSOR));
       attr = true;
     }
-    k_tile_sensor<ND, BS, FINER><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
+    if (D.all_pow2) k_tile_sensor<ND, BS, FINER, true><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
+    else k_tile_sensor<ND, BS, FINER, false><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
     LAUNCH_CHECK();
   } else {
     if (n_flux == 0) return IBX_OK;

@@ -297,6 +297,13 @@ int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, 
 typedef struct ibx_bc_spec { int boundary; int normal_flow; int n_pinf; float Pinf[5]; } ibx_bc_spec;
 int ibx_euler_step_host(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
                         const float* Q_host, float* R_host, float* cfl_host);
+/* The same call split in two so that consecutive, independent evaluations (finite-difference JVP probes of
+ * src/point_implicit.jl:98-114, Hutchinson samples :18-47) overlap: `begin` enqueues H2D(Q) -> ghost updates ->
+ * residual -> D2H(R, cfl) on slot 0 or 1 and returns; `end` blocks until the slot's results are in the host buffers.
+ * The host buffers must stay valid (and pinned, for the copies to be asynchronous) until `end`. */
+int ibx_euler_step_host_begin(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                              const float* Q_host, float* R_host, float* cfl_host, int slot);
+int ibx_euler_step_host_end(ibx_ctx* c, int slot);
 
 /* ------------------------------------------------------------------ multi-GPU (one rank per GPU) */
 /* Rank r owns the contiguous cell range of its blocks; halo = cells of other ranks within the 2-deep

@@ -112,6 +112,21 @@ def test_end_to_end_host_call_and_properties(get_case, ib):
     ib.ghost_update_euler(c.dom, fl, Q, bcs)
     ib.residual_euler(c.dom, fl, Q, R, cf)
     assert np.array_equal(R.to_host(), R_h) and np.array_equal(cf.to_host(), c_h)
+    # the split form on alternating slots (independent evaluations in flight) delivers the same bits per evaluation
+    Qp = [ib.pinned_empty((N, 5)) for _ in range(2)]
+    Qp[0][...] = Q0
+    Qp[1][...] = Q0 * F32(1.001)
+    Rs, cs = [ib.pinned_empty((N, 5)) for _ in range(2)], [ib.pinned_empty((N,)) for _ in range(2)]
+    ib.euler_step_host_begin(c.dom, fl, bcs, Qp[0], Rs[0], cs[0], 0)
+    ib.euler_step_host_begin(c.dom, fl, bcs, Qp[1], Rs[1], cs[1], 1)
+    with pytest.raises(ib.IbxError):
+        ib.euler_step_host_begin(c.dom, fl, bcs, Qp[0], Rs[0], cs[0], 0)      # slot 0 is still in flight
+    ib.euler_step_host_end(0)
+    ib.euler_step_host_end(1)
+    assert np.array_equal(Rs[0], R_h) and np.array_equal(cs[0], c_h)
+    R_2, c_2 = np.zeros((N, 5), F32, order="F"), np.zeros(N, F32)
+    ib.euler_step_host(c.dom, fl, bcs, Qp[1], R_2, c_2)
+    assert np.array_equal(Rs[1], R_2) and np.array_equal(cs[1], c_2) and not np.array_equal(R_2, R_h)
     # uniform free stream: the flux divergence vanishes to rounding everywhere
     a = np.sqrt(1.4 * 283.0 * 288.15)
     Pu = np.tile(np.array([101325.0, 288.15, 0.5 * a, 10.0, -5.0], F32), (N, 1))
