@@ -36,6 +36,9 @@ struct ibx_ctx {
     bool busy = false;
   } e2e[2];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  // side streams of the fused residual: the irregular-block passes run beside the regular-block kernel
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};
   // NCCL
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -51,7 +54,7 @@ float* ensure_scratch(ibx_ctx* c, int64_t nfloats);
 // pencil-marching flux pass (march.cu)
 bool march_supported(const ibx_domain& D);
 int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,
-               const float* S, float* R, float* cfl, const double* GF, const float* GC);
+               const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st);
 
 #define CU(call)                                                                      \
   do {                                                                                \

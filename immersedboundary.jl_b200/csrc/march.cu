@@ -278,7 +278,7 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
 
 template <int FLUX, int SEG, int HYB>
 int launch_march(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
-                 float* R, float* cfl, const double* GF, const float* GC) {
+                 float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
   using C = MarchCfg<SEG>;
   static bool attr = false;
   if (!attr) {
@@ -286,17 +286,17 @@ int launch_march(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, 
     CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  k_march_flux<FLUX, SEG, HYB><<<n, C::NT, C::SMEM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  k_march_flux<FLUX, SEG, HYB><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
 }
 
 template <int FLUX, int SEG>
 int launch_march_h(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, const float* P,
-                   const float* S, float* R, float* cfl, const double* GF, const float* GC) {
-  if (hyb == 0) return launch_march<FLUX, SEG, 0>(c, D, blocks, n, f, P, S, R, cfl, GF, GC);
-  if (hyb == 1) return launch_march<FLUX, SEG, 1>(c, D, blocks, n, f, P, S, R, cfl, GF, GC);
-  return launch_march<FLUX, SEG, 2>(c, D, blocks, n, f, P, S, R, cfl, GF, GC);
+                   const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
+  if (hyb == 0) return launch_march<FLUX, SEG, 0>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (hyb == 1) return launch_march<FLUX, SEG, 1>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  return launch_march<FLUX, SEG, 2>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
 }
 
 }  // namespace
@@ -308,16 +308,16 @@ bool march_supported(const ibx_domain& D) { return D.nd == 3 && D.block_size == 
 // Marching flux pass over the listed blocks.  hyb: 0 regular, 1 irregular without / 2 with finer neighbours; for
 // hyb != 0 the fluxes of the general faces are read from (GF, GC), laid out by k_hyb_flux MODE 1 (tile.cu).
 int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,
-               const float* S, float* R, float* cfl, const double* GF, const float* GC) {
+               const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
   if (n == 0) return IBX_OK;
   const char* e = getenv("IBX_MARCH_SEG");   // threads per pencil (1 or 2); 2 measured faster on C4
   const int seg = e && atoi(e) == 1 ? 1 : 2;
   if (flux_kind == 0) {
-    if (seg == 1) return launch_march_h<0, 1>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC);
-    return launch_march_h<0, 2>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC);
+    if (seg == 1) return launch_march_h<0, 1>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
+    return launch_march_h<0, 2>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
   }
-  if (seg == 1) return launch_march_h<1, 1>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC);
-  return launch_march_h<1, 2>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC);
+  if (seg == 1) return launch_march_h<1, 1>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
+  return launch_march_h<1, 2>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
 }
 
 }  // namespace ibx

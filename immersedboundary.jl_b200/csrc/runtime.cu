@@ -109,6 +109,11 @@ int ibx_finalize(ibx_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  for (int k = 0; k < 2; ++k) {
+    if (c->aux_stream[k]) cudaStreamDestroy(c->aux_stream[k]);
+    if (c->aux_join[k]) cudaEventDestroy(c->aux_join[k]);
+  }
+  if (c->aux_fork) cudaEventDestroy(c->aux_fork);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   for (auto& S : c->e2e) {
     if (S.up) cudaEventDestroy(S.up);

@@ -1091,8 +1091,9 @@ k_hyb_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fac
 
 template <int ND, int BS, bool FINER, bool P2, int FLUX, int MODE>
 int launch_hyb_mode(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
-                    float* R, float* cfl, double* GF, float* GC) {
+                    float* R, float* cfl, double* GF, float* GC, cudaStream_t st = nullptr) {
   using C = HybCfg<ND, BS, FINER>;
+  if (!st) st = c->stream;
   static bool attr = false;
   constexpr size_t SM = MODE == 1 ? C::SMEM_GENERAL : C::SMEM;
   if (!attr) {
@@ -1100,7 +1101,7 @@ int launch_hyb_mode(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int 
     CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE><<<n, C::NT, SM, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE><<<n, C::NT, SM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
 }
@@ -1242,9 +1243,7 @@ int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   using CF = HybCfg<ND, BS, true>;
   constexpr int NV = CP::NV;
   int rc;
-  if ((rc = march_flux(c, D, D.d_blk_own_regular, D.n_own_regular, 0, f, flux_kind, P, S, R, cfl, nullptr, nullptr))) return rc;
   const int64_t sl_p = (int64_t)D.n_own_plain * ND * (4 * CP::FACE + CP::NX), sl_f = (int64_t)D.n_own_finer * ND * (4 * CF::FACE + CF::NX);
-  if (sl_p + sl_f == 0) return IBX_OK;
   const int64_t need = (sl_p + sl_f) * (NV * 2 + 1);  // floats: NV doubles + 1 float per slot
   if (need > c->scratch2_cap) {
     if (c->d_scratch2) cudaFree(c->d_scratch2);
@@ -1257,18 +1256,42 @@ int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   double* GFf = GFp + sl_p * NV;
   float* GCp = (float*)(GFf + sl_f * NV);
   float* GCf = GCp + sl_p;
+  // The three block classes are independent of each other: the two irregular ones (general-face pass, then marching)
+  // run on side streams beside the regular-block kernel, which fills the SMs their short launches leave idle.
+  if (!c->aux_fork) {
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaStreamCreateWithFlags(&c->aux_stream[k], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&c->aux_join[k], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+  }
+  const bool side = getenv("IBX_ONE_STREAM") == nullptr;
+  cudaStream_t sp = side ? c->aux_stream[0] : c->stream, sf = side ? c->aux_stream[1] : c->stream;
+  if (side) {
+    CU(cudaEventRecord(c->aux_fork, c->stream));
+    CU(cudaStreamWaitEvent(sp, c->aux_fork, 0));
+    CU(cudaStreamWaitEvent(sf, c->aux_fork, 0));
+  }
   if (D.n_own_plain) {
-    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, false, true, 0, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp);
-    else rc = launch_hyb_mode<ND, BS, false, true, 1, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp);
+    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, false, true, 0, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
+    else rc = launch_hyb_mode<ND, BS, false, true, 1, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
     if (rc) return rc;
+    if ((rc = march_flux(c, D, D.d_blk_own_plain, D.n_own_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp, sp))) return rc;
   }
   if (D.n_own_finer) {
-    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, true, true, 0, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf);
-    else rc = launch_hyb_mode<ND, BS, true, true, 1, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf);
+    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, true, true, 0, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
+    else rc = launch_hyb_mode<ND, BS, true, true, 1, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
     if (rc) return rc;
+    if ((rc = march_flux(c, D, D.d_blk_own_finer, D.n_own_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf, sf))) return rc;
   }
-  if ((rc = march_flux(c, D, D.d_blk_own_plain, D.n_own_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp))) return rc;
-  return march_flux(c, D, D.d_blk_own_finer, D.n_own_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf);
+  if ((rc = march_flux(c, D, D.d_blk_own_regular, D.n_own_regular, 0, f, flux_kind, P, S, R, cfl, nullptr, nullptr, c->stream))) return rc;
+  if (side) {
+    CU(cudaEventRecord(c->aux_join[0], sp));
+    CU(cudaEventRecord(c->aux_join[1], sf));
+    CU(cudaStreamWaitEvent(c->stream, c->aux_join[0], 0));
+    CU(cudaStreamWaitEvent(c->stream, c->aux_join[1], 0));
+  }
+  return IBX_OK;
 }
 
 template <int ND, int BS>
