@@ -13,7 +13,9 @@ from .domain import (Domain, Partition, Boundary, Surface, DeviceArray, Accumula
                      face_gradient, JST_sensor, MUSCL, impose_bc, multigrid, volume_integral, surface_integral,
                      at_offset)
 from .cfd import (Fluid, FlowBC, state2primitive, primitive2state, speed_of_sound, inviscid_fluxes,  # noqa: F401
+                  dynamic_viscosity, heat_conductivity, viscous_fluxes, JST_sensor_3pt, shock_sensor, pressure_coefficient,
+                  streamwise_direction, Reynolds_number, adjust_Reynolds,
                   residual_euler, ghost_update_euler, residual_advection, euler_step_host, euler_step_host_begin,
                   euler_step_host_end, pinned_empty)
 from .solver import FAS, Multigrid, PIPreconditioner, hutchinson_trick, Linearization, linearize, proj_along, solve  # noqa: F401
-from . import synthetic  # noqa: F401
+from . import synthetic, turbulence  # noqa: F401

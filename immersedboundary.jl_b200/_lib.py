@@ -36,7 +36,16 @@ class BCSpec(C.Structure):
     _fields_ = [("boundary", C.c_int), ("normal_flow", C.c_int), ("n_pinf", C.c_int), ("Pinf", C.c_float * 5)]
 
 
-_STRUCTS = {"ibx_region": Region, "ibx_surface": SurfaceSpec, "ibx_fluid": Fluid, "ibx_bc_spec": BCSpec}
+class Transport(C.Structure):
+    _fields_ = [("mu_ref", C.c_float), ("T_ref", C.c_float), ("S", C.c_float), ("nk", C.c_int), ("k", C.c_float * 4)]
+
+
+class WallParams(C.Structure):
+    _fields_ = [("kappa", C.c_float), ("C", C.c_float), ("A", C.c_float), ("beta", C.c_float), ("beta_star", C.c_float),
+                ("D", C.c_float), ("A_plus", C.c_float), ("omega", C.c_float), ("n_iter", C.c_int)]
+
+
+_STRUCTS = {"ibx_transport": Transport, "ibx_wall_params": WallParams, "ibx_region": Region, "ibx_surface": SurfaceSpec, "ibx_fluid": Fluid, "ibx_bc_spec": BCSpec}
 _OPAQUE = {"ibx_ctx", "ibx_stl", "ibx_dfield", "ibx_mesh", "ibx_domain", "ibx_accum", "void"}
 _SCALARS = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "float": C.c_float, "double": C.c_double,
             "ibx_array": C.c_int64, "char": C.c_char}

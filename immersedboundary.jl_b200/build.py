@@ -14,7 +14,7 @@ HOSTFLAGS = "-fPIC,-fopenmp,-ffp-contract=off,-Wall,-Wno-unused-variable,-Wno-un
 # The numerical kernels reproduce the reference's separate float32 roundings bit for bit: no FMA contraction.
 # (A residual is a small difference of large fluxes; a 1-ulp change of a flux moves it by ~1e-3 relative.)
 NOFMA = ["-fmad=false"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", HOSTFLAGS]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "--extended-lambda", "-Xcompiler", HOSTFLAGS]
 
 
 def _sources():
@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ, src + ".o")
         if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hm):
-            extra = NOFMA if src in ("ops.cu", "cfd.cu", "fused.cu", "tile.cu", "march.cu") else []
+            extra = NOFMA if src in ("ops.cu", "cfd.cu", "fused.cu", "tile.cu", "march.cu", "closures.cu") else []
             cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
             if src.endswith(".cpp"):
                 cmd = [NVCC] + COMMON + ["-x", "cu"] * 0 + ["-c", sp, "-o", op]

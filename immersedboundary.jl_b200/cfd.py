@@ -21,6 +21,12 @@ class Fluid:
     def c(self):
         return _lib.Fluid(float(self.R), float(self.gamma))
 
+    @property
+    def transport(self):
+        """Sutherland / conductivity constants as the ABI's ``ibx_transport``."""
+        k = (C.c_float * 4)(*([float(x) for x in self.k] + [0.0] * (4 - len(self.k))))
+        return _lib.Transport(float(self.mu_ref), float(self.T_ref), float(self.S), len(self.k), k)
+
 
 def _like(a):
     return DeviceArray(a.rows, a.cols, a.vector)
@@ -45,6 +51,88 @@ def speed_of_sound(fluid, T):
     a = _like(T)
     call("ibx_speed_of_sound", context(), fluid.c, T.h, a.h)
     return a
+
+
+def dynamic_viscosity(fluid, T):
+    """``dynamic_viscosity`` (Sutherland, ``src/cfd.jl:71-77``)."""
+    mu = _like(T)
+    call("ibx_dynamic_viscosity", context(), fluid.transport, T.h, mu.h)
+    return mu
+
+
+def heat_conductivity(fluid, T):
+    """``heat_conductivity`` (``src/cfd.jl:84-90``)."""
+    k = _like(T)
+    call("ibx_heat_conductivity", context(), fluid.transport, T.h, k.h)
+    return k
+
+
+def _handles(arrays):
+    return (C.c_int64 * len(arrays))(*[a.h for a in arrays])
+
+
+def _grad_table(g):
+    """nested ``g[i][j]`` = d u_i / d x_j (vectors) -> row-major handle table."""
+    nd = len(g)
+    assert all(len(r) == nd for r in g), "velocity-gradient matrix must be nd x nd"
+    return nd, _handles([g[i][j] for i in range(nd) for j in range(nd)])
+
+
+def viscous_fluxes(fluid, P, Pgrad, dim, mu_t=0.0):
+    """``viscous_fluxes(fluid, P, Pgrad, dim; μₜ)`` (``src/cfd.jl:664-736``): ``dim`` a 0-based axis or an N x nd
+    direction matrix; ``mu_t`` a scalar or a vector."""
+    F = _like(P)
+    normals = dim if isinstance(dim, DeviceArray) else None
+    mt = mu_t if isinstance(mu_t, DeviceArray) else None
+    call("ibx_viscous_fluxes", context(), fluid.transport, P.h, _handles(list(Pgrad)), -1 if normals is not None else int(dim),
+         normals.h if normals is not None else 0, mt.h if mt is not None else 0, C.c_float(0.0 if mt is not None else float(mu_t)), F.h)
+    return F
+
+
+def JST_sensor_3pt(Pim1, Pi, Pip1):
+    """Pointwise ``JST_sensor(Pim1, Pi, Pip1)`` (``src/cfd.jl:563-573``)."""
+    out = _like(Pi)
+    call("ibx_jst_sensor3", context(), Pim1.h, Pi.h, Pip1.h, out.h)
+    return out
+
+
+def shock_sensor(velocity_gradients):
+    """``shock_sensor`` (``src/cfd.jl:589-617``); ``velocity_gradients[i][j]`` = d u_i / d x_j."""
+    nd, tab = _grad_table(velocity_gradients)
+    out = _like(velocity_gradients[0][0])
+    call("ibx_shock_sensor", context(), nd, tab, out.h)
+    return out
+
+
+def pressure_coefficient(fluid, p, p_inf, M_inf):
+    """``pressure_coefficient`` (``src/cfd.jl:420-426``)."""
+    Cp = _like(p)
+    call("ibx_pressure_coefficient", context(), C.c_float(float(fluid.gamma)), p.h, C.c_float(float(p_inf)), C.c_float(float(M_inf)), Cp.h)
+    return Cp
+
+
+def streamwise_direction(alpha, beta=None):
+    """``streamwise_direction`` (``src/cfd.jl:399-409, 434-436``), angles in degrees."""
+    ca, sa = np.cos(np.radians(alpha)), np.sin(np.radians(alpha))
+    if beta is None:
+        return np.array([ca, sa])
+    cb, sb = np.cos(np.radians(beta)), np.sin(np.radians(beta))
+    return np.array([ca * cb, -ca * sb, sa])
+
+
+def Reynolds_number(fluid, P_inf, L_ref):
+    """``Reynolds_number`` (``src/cfd.jl:626-637``); host scalars, the viscosity through the device kernel."""
+    P_inf = np.asarray(P_inf, dtype=F32)
+    V = F32(np.sqrt(np.sum(P_inf[2:].astype(np.float64) ** 2)))
+    rho = P_inf[0] / (fluid.R * P_inf[1])
+    mu = dynamic_viscosity(fluid, DeviceArray.from_host(P_inf[1:2].copy())).to_host()[0]
+    return V * F32(L_ref) * rho / mu
+
+
+def adjust_Reynolds(fluid, P_inf, L_ref, Re):
+    """``adjust_Reynolds`` (``src/cfd.jl:645-654``): a new ``Fluid`` whose reference viscosity gives ``Re``."""
+    mu_ref = fluid.mu_ref * Reynolds_number(fluid, P_inf, L_ref) / F32(Re)
+    return Fluid(fluid.R, fluid.gamma, fluid.k, mu_ref, fluid.T_ref, fluid.S)
 
 
 def inviscid_fluxes(fluid, PL, PR, *args):

@@ -22,7 +22,8 @@ export Stereolitography, merge_points, feature_regions, DistanceField, Ball, Box
        at_owners, at_neighbors, at_faces, green_gauss, unsigned_green_gauss, cell_gradient, face_distance,
        owner_distance, neighbor_distance, face_gradient, JST_sensor, MUSCL, impose_bc!, multigrid, volume_integral,
        Fluid, FlowBC, state2primitive, primitive2state, speed_of_sound, inviscid_fluxes,
-       residual_euler!, ghost_update_euler!
+       residual_euler!, ghost_update_euler!, Transport, dynamic_viscosity, heat_conductivity, viscous_fluxes,
+       shock_sensor, shear_rate, Ducros_sensor, pressure_coefficient
 
 const libibx = get(ENV, "LIBIBX", joinpath(@__DIR__, "..", "libibx.so"))
 
@@ -380,6 +381,43 @@ residual_euler!(dom::Domain, fluid::Fluid, Q::IBXArray, R::IBXArray, cfl::IBXArr
 ghost_update_euler!(dom::Domain, fluid::Fluid, bname::String, bc::FlowBC, Q::IBXArray) = check(ccall(
     (:ibx_ghost_update_euler, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Fluid, Ptr{Float32}, Cint, Cint, Int64),
     context(), dom.h, dom.boundary_index[bname], fluid, bc.P, length(bc.P), bc.normal_flow, Q.h))
+
+# ------------------------------------------------------------------ transport, viscous fluxes, pointwise sensors (csrc/closures.cu)
+"Sutherland / conductivity constants as `ibx_transport` (isbits, passed by value)."
+struct Transport; μref::Float32; Tref::Float32; S::Float32; nk::Cint; k::NTuple{4, Float32}; end
+Transport(; μref = 1.716f-5, Tref = 273.15f0, S = 110.4f0, k = (0.00646f0, 6.468f-5)) =
+    Transport(μref, Tref, S, length(k), ntuple(i -> i <= length(k) ? Float32(k[i]) : 0.0f0, 4))
+for (jn, cn) in ((:dynamic_viscosity, :ibx_dynamic_viscosity), (:heat_conductivity, :ibx_heat_conductivity))
+    @eval function $jn(t::Transport, T::IBXArray)
+        out = similar(T)
+        check(ccall(($(QuoteNode(cn)), libibx), Cint, (Ptr{Cvoid}, Transport, Int64, Int64), context(), t, T.h, out.h)); out
+    end
+end
+"`viscous_fluxes(fluid, P, Pgrad, dim; μₜ)` (src/cfd.jl:664-736); `dim::Int` (1-based) or an N x nd direction matrix."
+function viscous_fluxes(t::Transport, P::IBXArray, Pgrad, dim::Union{Int, IBXArray}; μₜ::Union{Real, IBXArray} = 0.0f0)
+    F = similar(P); hs = Int64[g.h for g in Pgrad]
+    GC.@preserve hs check(ccall((:ibx_viscous_fluxes, libibx), Cint, (Ptr{Cvoid}, Transport, Int64, Ptr{Int64}, Cint, Int64, Int64, Cfloat, Int64),
+        context(), t, P.h, hs, dim isa Int ? dim - 1 : -1, dim isa Int ? 0 : dim.h, μₜ isa Real ? 0 : μₜ.h, μₜ isa Real ? Float32(μₜ) : 0.0f0, F.h)); F
+end
+function JST_sensor(Pim1::IBXArray, Pi::IBXArray, Pip1::IBXArray)
+    out = similar(Pi)
+    check(ccall((:ibx_jst_sensor3, libibx), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64), context(), Pim1.h, Pi.h, Pip1.h, out.h)); out
+end
+"velocity_gradients[i, j] = ∂uᵢ/∂xⱼ (matrix of vectors) -> row-major handle table"
+_grad_table(g::AbstractMatrix) = Int64[g[i, j].h for i in axes(g, 1) for j in axes(g, 2)]
+for (jn, cn) in ((:shock_sensor, :ibx_shock_sensor), (:shear_rate, :ibx_shear_rate), (:Ducros_sensor, :ibx_ducros_sensor))
+    @eval function $jn(g::AbstractMatrix)
+        out = similar(g[1, 1]); hs = _grad_table(g)
+        GC.@preserve hs check(ccall(($(QuoteNode(cn)), libibx), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Int64), context(), size(g, 1), hs, out.h)); out
+    end
+end
+function pressure_coefficient(fluid::Fluid, p::IBXArray, p∞::Real, M∞::Real)
+    out = similar(p)
+    check(ccall((:ibx_pressure_coefficient, libibx), Cint, (Ptr{Cvoid}, Cfloat, Int64, Cfloat, Cfloat, Int64), context(), fluid.γ, p.h, p∞, M∞, out.h)); out
+end
+# src/turbulence.jl: wall_function, Smagorinsky_νSGS, standard_kϵ, Wray_Agarwal, WALE_νSGS bind ibx_wall_function(_rey),
+# ibx_smagorinsky, ibx_standard_keps, ibx_wray_agarwal, ibx_wale the same way (argument lists in include/ibx.h; the Python
+# mirror immersedboundary.jl_b200/turbulence.py is the executable statement of those bindings).
 
 "`multigrid(dom)` (src/ImmersedBoundary.jl:1355-1407): coarse Domains by `ibx_mesh_from_blocks` + IDW transfer accumulators
 by `ibx_interpolator_build`; returns `(coarse_doms, prolongators, coarseners)` like the reference code (:1406)."

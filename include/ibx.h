@@ -248,6 +248,35 @@ int ibx_inviscid_fluxes_sensor(ibx_ctx* c, ibx_fluid f, ibx_array PL, ibx_array 
 int ibx_flowbc(ibx_ctx* c, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow, ibx_array P,
                ibx_array normals, ibx_array out);
 
+/* ------------------------------------------------------------------ pointwise closures around the residual */
+/* Sutherland / conductivity-polynomial constants of Fluid (src/cfd.jl:14-53): mu_ref, T_ref, S, k[0..nk-1] */
+typedef struct ibx_transport { float mu_ref, T_ref, S; int nk; float k[4]; } ibx_transport;
+int ibx_dynamic_viscosity(ibx_ctx* c, ibx_transport t, ibx_array T, ibx_array mu);   /* src/cfd.jl:71-77 */
+int ibx_heat_conductivity(ibx_ctx* c, ibx_transport t, ibx_array T, ibx_array k);    /* :84-90 */
+/* viscous_fluxes(fluid, P, Pgrad, dim; mu_t) (src/cfd.jl:664-736).  Pgrad: nd arrays shaped like P (gradient along
+ * each axis).  normals != 0: the `dim::AbstractMatrix` method (N x nd direction matrix), `dim` ignored.
+ * mu_t != 0: per-point eddy viscosity, else the scalar mu_t_scalar. */
+int ibx_viscous_fluxes(ibx_ctx* c, ibx_transport t, ibx_array P, const ibx_array* Pgrad, int dim, ibx_array normals,
+                       ibx_array mu_t, float mu_t_scalar, ibx_array F);
+int ibx_jst_sensor3(ibx_ctx* c, ibx_array Pim1, ibx_array Pi, ibx_array Pip1, ibx_array out);   /* :563-573 */
+/* g[i * nd + j] = d u_i / d x_j, nd * nd vectors (the reference's matrix of vectors) */
+int ibx_shock_sensor(ibx_ctx* c, int nd, const ibx_array* g, ibx_array out);                    /* :589-617 */
+int ibx_pressure_coefficient(ibx_ctx* c, float gamma, ibx_array p, float p_inf, float M_inf, ibx_array Cp);   /* :420-426 */
+/* src/turbulence.jl */
+typedef struct ibx_wall_params { float kappa, C, A, beta, beta_star, D, A_plus, omega; int n_iter; } ibx_wall_params;   /* :27-33 */
+int ibx_wall_function_rey(ibx_ctx* c, ibx_wall_params w, ibx_array Rey, ibx_array y_plus, ibx_array u_plus, ibx_array mu_plus,
+                          ibx_array k_plus, ibx_array dudy_plus);                                /* :27-72 */
+int ibx_wall_function(ibx_ctx* c, ibx_wall_params w, ibx_array y, ibx_array u, ibx_array nu, ibx_array u_tau, ibx_array nu_t,
+                      ibx_array k, ibx_array omega, ibx_array eps, ibx_array dudn);              /* :74-98 */
+int ibx_shear_rate(ibx_ctx* c, int nd, const ibx_array* g, ibx_array out);                       /* :110-124 */
+int ibx_smagorinsky(ibx_ctx* c, ibx_array Delta, ibx_array S, float Cs, ibx_array out);          /* :126-137 */
+int ibx_standard_keps(ibx_ctx* c, ibx_array k, ibx_array eps, ibx_array S, float Cmu, float sigma_k, float sigma_eps, float C1,
+                      float C2, ibx_array nu_k, ibx_array nu_eps, ibx_array Sk, ibx_array Seps, ibx_array nu_t);   /* :175-194 */
+int ibx_wray_agarwal(ibx_ctx* c, ibx_array R, ibx_array S, ibx_array gradR, ibx_array gradS, float sigma_R, float C1, float kappa,
+                     ibx_array nu_R, ibx_array S_out);                                           /* :222-241 */
+int ibx_ducros_sensor(ibx_ctx* c, int nd, const ibx_array* g, ibx_array out);                    /* :253-283 */
+int ibx_wale(ibx_ctx* c, ibx_array Delta, const ibx_array* g, float Cw, ibx_array out);          /* :292-337, 3-D only */
+
 /* ------------------------------------------------------------------ accumulators, IB ghost update (K8, K9) */
 /* out = acc(v)  (src/accumulator.jl:78-130); delta: subtract v[row] first (Delta = true) */
 int ibx_accumulate(ibx_ctx* c, const ibx_accum* a, ibx_array v, int delta, ibx_array out);

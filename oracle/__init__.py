@@ -24,4 +24,4 @@ Every function cites the reference file:line it follows (paths relative to the
 reference checkout root).
 """
 
-from . import accumulator, nninterp, mesher, cfd, domain, solver, mgrid, point_implicit, euler  # noqa: F401
+from . import accumulator, nninterp, mesher, cfd, domain, solver, mgrid, point_implicit, euler, turbulence  # noqa: F401

@@ -31,18 +31,51 @@ def speed_of_sound(fld, T):
     return np.sqrt(fld.gamma * fld.R * _clampT(T))
 
 
+def pow32(x, y):
+    """Float32 ``x ^ y`` as Julia evaluates it: in Float64 through exp2(log2|x| * y), rounded once
+    (``Base.Math.pow_body`` for Float16/Float32); integer exponents by repeated Float64 multiplication."""
+    x = np.asarray(x, dtype=F32).astype(np.float64)
+    if isinstance(y, (int, np.integer)):
+        r = np.ones_like(x)
+        for _ in range(int(y)):
+            r = r * x
+        return r.astype(F32)
+    with np.errstate(divide="ignore"):
+        return np.exp2(np.log2(np.abs(x)) * np.float64(F32(y))).astype(F32)
+
+
 def dynamic_viscosity(fld, T):
     """``dynamic_viscosity``, ``src/cfd.jl:71-77`` (note the exponent 2/3 of the reference)."""
     T = _clampT(T)
-    return fld.mu_ref * ((T / fld.T_ref) ** (F32(2.0) / F32(3))) * (fld.T_ref + fld.S) / (T + fld.S)
+    return fld.mu_ref * pow32(T / fld.T_ref, F32(2.0) / F32(3)) * (fld.T_ref + fld.S) / (T + fld.S)
 
 
 def heat_conductivity(fld, T):
     """``heat_conductivity``, ``src/cfd.jl:84-90``."""
     k = F32(0) * T
     for i, ki in enumerate(fld.k):
-        k = k + ki * T ** i
+        k = k + ki * pow32(T, i)
     return k
+
+
+def pressure_coefficient(fld, p, p_inf, M_inf):
+    """``pressure_coefficient``, ``src/cfd.jl:420-426``."""
+    return F32(2) * (p / F32(p_inf) - F32(1.0)) / (F32(M_inf) * F32(M_inf) * fld.gamma)
+
+
+def reynolds_number(fld, P_inf, L_ref):
+    """``Reynolds_number``, ``src/cfd.jl:626-637``."""
+    P_inf = np.asarray(P_inf, dtype=F32)
+    V = F32(np.sqrt(np.sum(P_inf[2:].astype(np.float64) ** 2)))
+    rho = P_inf[0] / (fld.R * P_inf[1])
+    mu = dynamic_viscosity(fld, P_inf[1:2])[0]
+    return V * F32(L_ref) * rho / mu
+
+
+def adjust_reynolds(fld, P_inf, L_ref, Re):
+    """``adjust_Reynolds``, ``src/cfd.jl:645-654``: a new fluid whose reference viscosity gives ``Re``."""
+    mu_ref = fld.mu_ref * reynolds_number(fld, P_inf, L_ref) / F32(Re)
+    return Fluid(fld.R, fld.gamma, fld.k, mu_ref, fld.T_ref, fld.S)
 
 
 def _half_sq(u):
@@ -175,8 +208,24 @@ def jst_sensor_3pt(Pim1, Pi, Pip1):
     return (np.abs(Pim1 + Pip1 - 2 * Pi) + e) / (np.abs(Pim1 - Pi) + np.abs(Pip1 - Pi) + e)
 
 
+def shock_sensor(vg):
+    """``shock_sensor``, ``src/cfd.jl:589-617``; ``vg[i][j]`` = d u_i / d x_j (vectors).  In 2-D the reference's
+    cyclic loop visits the single vorticity component twice; kept."""
+    e = F32(1e-14)
+    nd = len(vg)
+    vort = np.zeros_like(vg[0][0])
+    divu = np.zeros_like(vg[0][0])
+    for i in range(nd):
+        i1 = (i + 1) % nd
+        i2 = (i1 + 1) % nd
+        divu = divu + vg[i][i]
+        vort = vort + (vg[i2][i1] - vg[i1][i2]) ** 2
+    divu = divu * divu
+    return (divu + e) / (divu + vort + e)
+
+
 def viscous_fluxes(fld, P, Pgrad, dim, mu_t=F32(0.0)):
-    """``viscous_fluxes`` along a Cartesian ``dim`` (0-based), ``src/cfd.jl:664-736``."""
+    """``viscous_fluxes``, ``src/cfd.jl:664-736``: ``dim`` a 0-based axis or an (N, nd) direction matrix."""
     T = P[:, 1]
     mu = dynamic_viscosity(fld, T) + mu_t
     k = heat_conductivity(fld, T)
@@ -186,15 +235,24 @@ def viscous_fluxes(fld, P, Pgrad, dim, mu_t=F32(0.0)):
     for i in range(nd):
         divu = divu + vg(i, i)
     tau = lambda i, j: ((vg(i, j) + vg(j, i)) - (F32(2.0) / F32(3) if i == j else F32(0.0)) * divu) * mu
+    f = lambda i: Pgrad[i][:, 1] * k
     F = np.zeros_like(P)
-    F[:, 1] = F[:, 1] + Pgrad[dim][:, 1] * k
-    for j in range(nd):
-        F[:, 1] = F[:, 1] + tau(dim, j) * P[:, 2 + j]
-    for j in range(nd):
-        F[:, 2 + j] = F[:, 2 + j] + tau(dim, j)
+    if np.ndim(dim) == 0:
+        F[:, 1] = F[:, 1] + f(dim)
+        for j in range(nd):
+            F[:, 1] = F[:, 1] + tau(dim, j) * P[:, 2 + j]
+        for j in range(nd):
+            F[:, 2 + j] = F[:, 2 + j] + tau(dim, j)
+    else:
+        taud = []
+        for i in range(nd):
+            s = np.zeros_like(T)
+            for j in range(nd):
+                s = s + tau(i, j) * dim[:, j]
+            taud.append(s)
+        for j in range(nd):
+            F[:, 1] = F[:, 1] + f(j) * dim[:, j]
+            F[:, 1] = F[:, 1] + taud[j] * P[:, 2 + j]
+        for j in range(nd):
+            F[:, 2 + j] = F[:, 2 + j] + taud[j]
     return F
-
-
-def pressure_coefficient(fld, p, p_inf, M_inf):
-    """``pressure_coefficient``, ``src/cfd.jl:420-426``."""
-    return 2 * (p / p_inf - F32(1.0)) / (M_inf ** 2 * fld.gamma)
