@@ -25,17 +25,23 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "lts__t_bytes.sum", "sass__inst_executed_shared_loads", "sass__inst_executed_global_loads"]
 
-def report(rep, out, cells=None):
+def report(rep, out, cells=None, idx=0):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    H, U, V = rows[0], rows[1], rows[2]
+    H, U, V = rows[0], rows[1], rows[2 + idx]
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
+    starts = [i for i, r in enumerate(srows) if r and r[0] == "Kernel Name"]   # one table per captured launch
+    want = V[H.index('Kernel Name')].split('(')[0]
+    pick = [k for k, i in enumerate(starts) if srows[i][1].replace('(int)', '').replace('(bool)', '').split('(')[0] == want] or [idx]
+    k = pick[0]
+    srows = srows[starts[k]:(starts[k + 1] if k + 1 < len(starts) else len(srows))]
     SH = srows[1]
     si, ei = SH.index("Source"), SH.index("Instructions Executed")
     cols = [(i, h) for i, h in enumerate(SH) if h.startswith("stall_") and "Not Issued" not in h]
     op, st, tot = collections.Counter(), collections.Counter(), 0
     for r in srows[2:]:
+        if r and r[0] in ("Kernel Name", "Address"): break   # multi-launch report: only the first launch is summarised
         if len(r) <= ei: continue
         m = r[si].strip().split()
         if not m: continue
@@ -48,7 +54,7 @@ def report(rep, out, cells=None):
         for w in WANT:
             if w in H:
                 i = H.index(w); fh.write(f"{w:72s} {U[i]:>16s} {V[i]}\n")
-        fh.write(f"SASS instructions in kernel: {len(srows) - 2}\n")
+        fh.write(f"warp instructions executed (source page): {tot}\n")
         if cells:
             fh.write(f"thread-instructions per cell: {tot * 32 / cells:.1f}  (cells in this launch: {cells})\n")
             i = H.index("dram__bytes_read.sum"); j = H.index("dram__bytes_write.sum")
@@ -64,4 +70,4 @@ def report(rep, out, cells=None):
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "launches": launches(sys.argv[2], sys.argv[3])
-    else: report(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
+    else: report(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4] != '-' else None, int(sys.argv[5]) if len(sys.argv) > 5 else 0)
