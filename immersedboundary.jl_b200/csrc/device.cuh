@@ -51,6 +51,9 @@ ibx_domain* find_domain(const ibx_domain* d);
 ibx_accum* find_accum(const ibx_accum* a);
 bool get_array(ibx_ctx* c, ibx_array h, ibx_ctx::Arr& out);
 float* ensure_scratch(ibx_ctx* c, int64_t nfloats);
+// general faces of irregular blocks (gen.cu)
+int general_faces(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, bool finer, ibx_fluid f, int flux_kind,
+                  const float* P, const float* S, double* GF, float* GC, cudaStream_t st);
 // pencil-marching flux pass (march.cu)
 bool march_supported(const ibx_domain& D);
 int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,

@@ -1272,14 +1272,18 @@ int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
     CU(cudaStreamWaitEvent(sp, c->aux_fork, 0));
     CU(cudaStreamWaitEvent(sf, c->aux_fork, 0));
   }
+  // IBX_GEN_OLD=1: the general faces through the generic neighbour-list code of k_hyb_flux MODE 1 (cross-check of gen.cu)
+  const bool gen_old = getenv("IBX_GEN_OLD") != nullptr;
   if (D.n_own_plain) {
-    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, false, true, 0, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
+    if (!gen_old) rc = general_faces(c, D, D.d_blk_own_plain, D.n_own_plain, false, f, flux_kind, P, S, GFp, GCp, sp);
+    else if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, false, true, 0, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
     else rc = launch_hyb_mode<ND, BS, false, true, 1, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
     if (rc) return rc;
     if ((rc = march_flux(c, D, D.d_blk_own_plain, D.n_own_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp, sp))) return rc;
   }
   if (D.n_own_finer) {
-    if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, true, true, 0, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
+    if (!gen_old) rc = general_faces(c, D, D.d_blk_own_finer, D.n_own_finer, true, f, flux_kind, P, S, GFf, GCf, sf);
+    else if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, true, true, 0, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
     else rc = launch_hyb_mode<ND, BS, true, true, 1, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
     if (rc) return rc;
     if ((rc = march_flux(c, D, D.d_blk_own_finer, D.n_own_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf, sf))) return rc;

@@ -29,8 +29,9 @@ R, cfl = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True)
 print(f"cells {N}  blocks {msh.nblocks}  flux {flux}", flush=True)
 ms = C.c_float()
 ref = None
-for label, env in (("tile kernels", {"IBX_NO_MARCH": "1"}), ("march SEG=1", {"IBX_MARCH_SEG": "1"}), ("march SEG=2", {"IBX_MARCH_SEG": "2"})):
-    for k in ("IBX_NO_MARCH", "IBX_MARCH_SEG"):
+for label, env in (("tile kernels", {"IBX_NO_MARCH": "1"}), ("march, generic general faces", {"IBX_GEN_OLD": "1"}),
+                   ("march SEG=1", {"IBX_MARCH_SEG": "1"}), ("march SEG=2", {"IBX_MARCH_SEG": "2"})):
+    for k in ("IBX_NO_MARCH", "IBX_MARCH_SEG", "IBX_GEN_OLD"):
         os.environ.pop(k, None)
     os.environ.update(env)
     R.fill(0.0); cfl.fill(0.0)
@@ -42,7 +43,7 @@ for label, env in (("tile kernels", {"IBX_NO_MARCH": "1"}), ("march SEG=1", {"IB
         ib.residual_euler(dom, fluid, Q, R, cfl, flux=flux)
     ib._lib.call("ibx_timer_stop", ctx, C.byref(ms))
     Rh, ch = R.to_host(), cfl.to_host()
-    msg = f"{label:14s} {ms.value / reps:8.3f} ms/call  {N / (ms.value / reps) / 1e6:8.2f} G cell-updates/s"
+    msg = f"{label:30s} {ms.value / reps:8.3f} ms/call  {N / (ms.value / reps) / 1e6:8.2f} G cell-updates/s"
     if ref is None:
         ref = (Rh, ch)
     else:
