@@ -54,6 +54,8 @@ float* ensure_scratch(ibx_ctx* c, int64_t nfloats);
 // general faces of irregular blocks (gen.cu)
 int general_faces(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, bool finer, ibx_fluid f, int flux_kind,
                   const float* P, const float* S, double* GF, float* GC, cudaStream_t st);
+int sensor_direct(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* p, float* S);
+int sensor_regular(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* p, float* S);
 // pencil-marching flux pass (march.cu)
 bool march_supported(const ibx_domain& D);
 int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,

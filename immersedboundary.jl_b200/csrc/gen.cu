@@ -170,9 +170,147 @@ k_gen_faces(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
   }
 }
 
+// JST sensor D = JST_sensor(part, p) with dim = 0 (src/ImmersedBoundary.jl:1077-1097) for every cell of the listed
+// blocks, straight from global memory: a cell reads its 6 face neighbours (1, or 4 quarter-weighted fine cells across a
+// finer contact; none across the domain box) through L1 -- p is a single 2 KB run per block, so the shared-memory tile
+// and its barrier bought nothing but latency.  Same differences, same order, same bits as k_reg_sensor / k_tile_sensor.
+template <bool P2>
+__global__ void __launch_bounds__(256)
+k_sensor_direct(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
+                const float* __restrict__ p, float* __restrict__ D) {
+  __shared__ FaceInfo fi[2 * ND];
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  if (tid < 2 * ND) fill_face_info<ND, BS>(fi[tid], faces[b * (2 * ND) + tid], 0, bh[b * ND + (tid >> 1)]);
+  __syncthreads();
+  const int64_t cell0 = b * CPB;
+  float h[ND], ih[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) { h[d] = bh[b * ND + d]; ih[d] = 1.0f / h[d]; }
+#pragma unroll
+  for (int rep = 0; rep < CPB / 256; ++rep) {
+    const int l = tid + rep * 256;
+    int ii[3];
+    split<ND, BS>(l, ii);
+    const float pc = p[cell0 + l];
+    float nu = 1e-7f;
+    int stride = 1;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float g[2], a[2];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        float accg = 0.0f, acca = 0.0f;
+        const bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
+        if (inner) {
+          const float fd = side ? p[cell0 + l + stride] - pc : pc - p[cell0 + l - stride];   // p_neighbour - p_owner
+          accg = fd;
+          acca = fabsf(fd);
+        } else {
+          const FaceInfo& F = fi[2 * d + side];
+          const int a1 = ii[T1(d)], a2 = ii[T2(d)];
+          if (F.kind == 1 || F.kind == 2) {
+            const int sh = F.kind == 2 ? 1 : 0;
+            const float pn = p[halo_cell<ND, BS>(F, d, side, a1 >> sh, a2 >> sh, 0, CPB)];
+            const float fd = side ? pn - pc : pc - pn;
+            accg = fd;
+            acca = fabsf(fd);
+          } else if (F.kind == 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float pn = p[halo_cell<ND, BS>(F, d, side, 2 * a1 + (q & 1), 2 * a2 + (q >> 1), 0, CPB)];
+              const float fd = side ? pn - pc : pc - pn;
+              accg = q == 0 ? fd * 0.25f : accg + fd * 0.25f;
+              acca = q == 0 ? fabsf(fd) * 0.25f : acca + fabsf(fd) * 0.25f;
+            }
+          }   // kind 0, box face: owner == neighbour, difference 0
+        }
+        g[side] = accg;
+        a[side] = acca;
+      }
+      const float gg = P2 ? (g[1] - g[0]) * ih[d] : (g[1] - g[0]) / h[d], ugg = P2 ? (a[1] + a[0]) * ih[d] : (a[1] + a[0]) / h[d];
+      nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ugg));
+      stride *= BS;
+    }
+    D[cell0 + l] = nu;
+  }
+}
+
+// JST sensor of REGULAR blocks (all six neighbours same level): the (BS + 2)^3 tile of p of k_reg_sensor (tile.cu), staged
+// with three vector loads per thread that are all in flight before the first store (own cells as float4, the x-face
+// layers as scalars, the y / z-face layers as float4) instead of five dependent load -> store rounds.  Same bits.
+template <bool P2>
+__global__ void __launch_bounds__(128)
+k_reg_sensor8(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
+              const float* __restrict__ p, float* __restrict__ D) {
+  constexpr int PD = BS + 2, PD2 = PD * PD;
+  __shared__ float sp[PD * PD * PD];
+  const int64_t b = blocks[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int64_t cell0 = b * CPB;
+  {
+    const int l = 4 * tid;
+    const float4 own = *reinterpret_cast<const float4*>(p + cell0 + l);
+    const int side = tid >> 6, pn = tid & 63;
+    const float xf = p[(int64_t)faces[b * 6 + side].nb[0] * CPB + (side ? 0 : BS - 1) + 8 * pn];
+    float4 yz = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int isz = tid >> 5 & 1, s2 = (tid >> 4) & 1, q = tid & 15, xh = (q & 1) * 4, r = q >> 1;
+    if (tid < 64) {
+      const int64_t nb = faces[b * 6 + 2 + 2 * isz + s2].nb[0];
+      yz = *reinterpret_cast<const float4*>(p + nb * CPB + (isz ? (s2 ? 0 : 64 * (BS - 1)) + 8 * r : (s2 ? 0 : 8 * (BS - 1)) + 64 * r) + xh);
+    }
+    float* t = sp + ((l & 7) + 1) + PD * (((l >> 3) & 7) + 1) + PD2 * ((l >> 6) + 1);
+    t[0] = own.x; t[1] = own.y; t[2] = own.z; t[3] = own.w;
+    sp[(side ? BS + 1 : 0) + PD * ((pn & 7) + 1) + PD2 * ((pn >> 3) + 1)] = xf;
+    if (tid < 64) {
+      float* u = isz ? sp + (xh + 1) + PD * (r + 1) + PD2 * (s2 ? BS + 1 : 0) : sp + (xh + 1) + PD * (s2 ? BS + 1 : 0) + PD2 * (r + 1);
+      u[0] = yz.x; u[1] = yz.y; u[2] = yz.z; u[3] = yz.w;
+    }
+  }
+  __syncthreads();
+  float h[ND], ih[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) { h[d] = bh[b * ND + d]; ih[d] = 1.0f / h[d]; }
+#pragma unroll
+  for (int rep = 0; rep < CPB / 128; ++rep) {
+    const int l = tid + rep * 128;
+    const int s = ((l & 7) + 1) + PD * (((l >> 3) & 7) + 1) + PD2 * ((l >> 6) + 1);
+    const float pc = sp[s];
+    float nu = 1e-7f;
+    int ss = 1;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const float fh = sp[s + ss] - pc, fl = pc - sp[s - ss];
+      const float gg = P2 ? (fh - fl) * ih[d] : (fh - fl) / h[d];
+      const float ug = P2 ? (fabsf(fh) + fabsf(fl)) * ih[d] : (fabsf(fh) + fabsf(fl)) / h[d];
+      nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ug));
+      ss *= PD;
+    }
+    D[cell0 + l] = nu;
+  }
+}
+
 }  // namespace
 
 namespace ibx {
+
+// JST sensor of the listed REGULAR 8^3 blocks (3-D)
+int sensor_regular(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* p, float* S) {
+  if (n == 0) return IBX_OK;
+  if (D.all_pow2) k_reg_sensor8<true><<<n, 128, 0, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, p, S);
+  else k_reg_sensor8<false><<<n, 128, 0, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, p, S);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
+
+// JST sensor of the listed 8^3 blocks (3-D)
+int sensor_direct(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* p, float* S) {
+  if (n == 0) return IBX_OK;
+  if (D.all_pow2) k_sensor_direct<true><<<n, 256, 0, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, p, S);
+  else k_sensor_direct<false><<<n, 256, 0, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, p, S);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
 
 // General-face pass over the listed irregular blocks; finer: the list's blocks have finer neighbours (scratch layout
 // with the fine-face slots).  st: the stream to launch on.

@@ -1303,16 +1303,27 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   int64_t N = D.ncells;
   k_prim<ND><<<grid_for(N, 256, c->sm_count, 16), 256, 0, c->stream>>>(f, Q, P, N);
   LAUNCH_CHECK();
-  int rc;
+  int rc = IBX_OK;
   // sensor on every local block (owned + halo blocks of a shard), fluxes on the owned blocks only
-  if (D.n_all_regular) {
+  bool direct = false;
+  if constexpr (ND == 3 && BS == 8) direct = getenv("IBX_SENSOR_TILES") == nullptr;   // IBX_SENSOR_TILES=1: the tile kernels (cross-check)
+  if (direct) {
+    if ((rc = sensor_regular(c, D, D.d_blk_all_regular, D.n_all_regular, P, S))) return rc;
+  } else if (D.n_all_regular) {
     using RC = RegCfg<ND, BS>;
     if (D.all_pow2) k_reg_sensor<ND, BS, true><<<D.n_all_regular, RC::NT, 0, c->stream>>>(D.d_blk_all_regular, D.d_block_faces, D.d_block_h, P, S);
     else k_reg_sensor<ND, BS, false><<<D.n_all_regular, RC::NT, 0, c->stream>>>(D.d_blk_all_regular, D.d_block_faces, D.d_block_h, P, S);
     LAUNCH_CHECK();
   }
-  if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
-  if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+  // irregular blocks: straight from global memory (gen.cu; 0.10 ms instead of 0.25 ms on C4 -- for regular blocks the
+  // lean tile kernel above stays ahead, 0.22 vs 0.38 ms: boundary cells make up 58 % of a block)
+  if (direct) {
+    if ((rc = sensor_direct(c, D, D.d_blk_all_plain, D.n_all_plain, P, S))) return rc;
+    if ((rc = sensor_direct(c, D, D.d_blk_all_finer, D.n_all_finer, P, S))) return rc;
+  } else {
+    if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+    if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+  }
   // 3-D 8^3 blocks with power-of-two spacings: pencil-marching kernel (march.cu) on every owned block; the general
   // faces of the irregular blocks are computed first (MODE 1) and handed over through a global scratch
   if constexpr (ND == 3 && BS == 8) {
