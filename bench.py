@@ -210,7 +210,7 @@ def run_ours(args):
             dom.halo_exchange(Q)
         ib.ghost_update_euler(dom, fluid, Q, bcs)
         if world > 1:
-            dom.halo_exchange(Q)
+            dom.halo_begin(Q)      # completed inside residual_euler, behind the conversion of the owned rows
         ib.residual_euler(dom, fluid, Q, R, cfl)
 
     def barrier():
@@ -299,8 +299,32 @@ def run_ours(args):
                "serial_single_call": {"value": n_global * k / dt_serial, "ms_per_step": dt_serial / k * 1e3, "steps": k,
                                       "api": "ibx_euler_step_host"}}
     else:
-        e2e = {"value": None, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "end-to-end host-buffer path is measured at N=1 only"}
+        # every rank: H2D of its shard's state (owned + halo rows) from pinned memory, the sharded step (halo exchange,
+        # ghost update, halo exchange, residual), D2H of its residual and CFL arrays; max over ranks
+        R_host, c_host = ib.pinned_empty((n_local, 5)), ib.pinned_empty((n_local,))
+
+        def e2e_step():
+            Q.upload(Q_host)
+            step()
+            ib._lib.call("ibx_array_download", ctx, R.h, ib._lib.ptr(R_host))
+            ib._lib.call("ibx_array_download", ctx, cfl.h, ib._lib.ptr(c_host))
+
+        e2e_step()
+        k = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        barrier()
+        import torch
+        t = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        hb = torch.tensor([float(Q_host.nbytes), float(R_host.nbytes + c_host.nbytes)], device="cuda")
+        dist.all_reduce(hb)
+        e2e = {"value": n_global * k / dt, "unit": "cell-updates/s", "h2d_bytes_per_step": int(hb[0].item()),
+               "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": dt / k * 1e3, "steps": k,
+               "api": "ibx_array_upload + sharded step + ibx_array_download on every rank (C ABI, pinned host buffers)"}
 
     if world > 1:
         ib._lib.call("ibx_comm_finalize", ctx)

@@ -165,6 +165,7 @@ int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
     }
   }
   CU(cudaEventRecord(c->ev_halo, c->comm_stream));
+  c->halo_pending = ah;
   return IBX_OK;
 }
 
@@ -173,6 +174,7 @@ int ibx_halo_end(ibx_ctx* c, const ibx_domain* d, ibx_array a) {
   (void)d;
   (void)a;
   CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  c->halo_pending = 0;
   return IBX_OK;
 }
 

@@ -14,6 +14,7 @@ struct ibx_ctx {
   cudaStream_t comm_stream = nullptr;  // halo exchange / copies
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_halo = nullptr, ev_ready = nullptr;
   int64_t launches = 0;
+  int64_t halo_pending = 0;   // array handle of a posted, not yet completed halo exchange (ibx_halo_begin / _end)
   bool poisoned = false;
   struct Arr { float* p; int64_t rows, cols; bool f64; };  // f64: the buffer holds doubles (HLL fluxes, src/cfd.jl:504-507)
   std::unordered_map<int64_t, Arr> arrays;

@@ -487,7 +487,14 @@ int ibx_residual_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_ki
   // tile kernels (one CTA per block, shared-memory staging) for power-of-two blocks; IBX_GENERIC=1 forces the
   // gather kernels (kept as the fallback for other block sizes and as a cross-check)
   const bool force_generic = getenv("IBX_GENERIC") != nullptr;
-  if (tile_supported(D) && !force_generic) return residual_euler_tiles(c, D, f, flux_kind, Q.p, P, S, R.p, CF.p);
+  const bool tiles = tile_supported(D) && !force_generic;
+  // a posted halo exchange (ibx_halo_begin without ibx_halo_end): the tile path overlaps it with the conversion of the
+  // owned rows when it is Q's; anything else waits for it here
+  if (c->halo_pending && (!tiles || c->halo_pending != Qh)) {
+    CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    c->halo_pending = 0;
+  }
+  if (tiles) return residual_euler_tiles(c, D, f, flux_kind, Q.p, P, S, R.p, CF.p);
   Topo T = make_topo(D);
   int g = fused_grid(c, N);
   if (D.nd == 2) {

@@ -1191,8 +1191,8 @@ k_reg_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
 
 // Q -> P, elementwise (src/cfd.jl:137-151)
 template <int ND>
-__global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n, int64_t i0, int64_t i1) {
+  for (int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
     float q[ND + 2], p[ND + 2];
 #pragma unroll
     for (int v = 0; v < ND + 2; ++v) q[v] = Q[(int64_t)v * n + i];
@@ -1301,8 +1301,26 @@ int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
 template <int ND, int BS>
 int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S, float* R, float* cfl) {
   int64_t N = D.ncells;
-  k_prim<ND><<<grid_for(N, 256, c->sm_count, 16), 256, 0, c->stream>>>(f, Q, P, N);
-  LAUNCH_CHECK();
+  if (c->halo_pending && D.shard.active && D.shard.n_owned <= N) {
+    // a halo exchange of Q is in flight (ibx_halo_begin without ibx_halo_end): convert the owned rows while it runs,
+    // then wait for it and convert the halo rows
+    const int64_t no = D.shard.n_owned;   // owned rows come first, then the halo rows
+    k_prim<ND><<<grid_for(no, 256, c->sm_count, 16), 256, 0, c->stream>>>(f, Q, P, N, 0, no);
+    LAUNCH_CHECK();
+    CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    c->halo_pending = 0;
+    if (N > no) {
+      k_prim<ND><<<grid_for(N - no, 256, c->sm_count, 16), 256, 0, c->stream>>>(f, Q, P, N, no, N);
+      LAUNCH_CHECK();
+    }
+  } else {
+    if (c->halo_pending) {
+      CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+      c->halo_pending = 0;
+    }
+    k_prim<ND><<<grid_for(N, 256, c->sm_count, 16), 256, 0, c->stream>>>(f, Q, P, N, 0, N);
+    LAUNCH_CHECK();
+  }
   int rc = IBX_OK;
   // sensor on every local block (owned + halo blocks of a shard), fluxes on the owned blocks only
   bool direct = false;

@@ -490,6 +490,14 @@ class Domain:
         call("ibx_halo_begin", context(), self._h, a.h)
         call("ibx_halo_end", context(), self._h, a.h)
 
+    def halo_begin(self, a):
+        """Post the exchange only.  ``residual_euler`` on the same array completes it after converting the owned rows
+        (the exchange then overlaps that kernel); any other consumer must call ``halo_end`` first."""
+        call("ibx_halo_begin", context(), self._h, a.h)
+
+    def halo_end(self, a):
+        call("ibx_halo_end", context(), self._h, a.h)
+
     def send_lists(self):
         out = {}
         n = self.shard_info["nranks"]

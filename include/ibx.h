@@ -349,7 +349,9 @@ int ibx_halo_lists(const ibx_domain* local, int peer, int32_t* send_local, int32
 /* tell this rank which of its cells `peer` needs (GLOBAL ids, in the peer's unpack order = recv_local order);
  * the host program moves these lists between ranks (torch.distributed / MPI / files) before ibx_domain_upload */
 int ibx_shard_set_send(ibx_domain* local, int peer, int64_t n, const int32_t* global_ids);
-/* exchange the halo rows of `a` (n_owned + n_halo rows): pack -> ncclSend/Recv -> unpack, on the comm stream */
+/* exchange the halo rows of `a` (n_owned + n_halo rows): pack -> ncclSend/Recv -> unpack, on the comm stream.
+ * ibx_residual_euler on the same array completes a posted exchange itself, after converting the owned rows (so the
+ * exchange overlaps that kernel); every other consumer calls ibx_halo_end first. */
 int ibx_halo_begin(ibx_ctx* c, const ibx_domain* local, ibx_array a);
 int ibx_halo_end(ibx_ctx* c, const ibx_domain* local, ibx_array a);
 int ibx_allreduce(ibx_ctx* c, int op /* 0 sum 1 max 2 min */, double* inout, int n);

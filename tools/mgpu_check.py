@@ -63,7 +63,7 @@ print(f"rank {rank}: after first exchange: needed rows correct = {np.array_equal
 for _ in range(2):  # twice: the second pass sees ghost values updated (and exchanged) by the first
     loc.halo_exchange(Ql)
     ib.ghost_update_euler(loc, fl, Ql, bcs)
-    loc.halo_exchange(Ql)
+    loc.halo_begin(Ql)      # completed inside residual_euler (overlapped with the owned-row conversion)
     ib.residual_euler(loc, fl, Ql, Rl, cl)
 own = l2g[:n_owned]
 okR = np.array_equal(Rl.to_host()[:n_owned], Rg.to_host()[own])
