@@ -28,7 +28,10 @@ for label, generic in (("tile", False), ("generic", True)):
     err = np.abs(Rg - Ro) / scale
     e = err.max(axis=1)
     bad = np.flatnonzero(e > 1e-5)
+    ndiff = int((Rg != Ro).sum())
+    ulp = np.abs(Rg.view(np.int32).astype(np.int64) - Ro.astype(F32).view(np.int32).astype(np.int64))
     print(f"== {label}: max scaled err {e.max():.3e}; cells with err > 1e-5: {len(bad)} of {N}; cfl max rel err {np.abs(cg / co - 1).max():.3e}")
+    print(f"   values that differ at all: {ndiff} of {Rg.size} ({ndiff / Rg.size:.2e}); largest difference {int(ulp.max())} ulp")
     if len(bad):
         blk = bad // cpb
         loc = bad % cpb
