@@ -73,8 +73,8 @@ def test_fused_matches_per_operator_path(get_case, ib):
     R, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True)
     ib.residual_euler(c.dom, fl, Q, R, cf)
     rel, scaled = _rel_err(R.to_host(), R1)
-    # both paths keep the reference's Float64 flux and Green-Gauss sums (src/cfd.jl:504-507); the fused kernels
-    # replace the Float64 divisions by reciprocals (1e-16), visible at most as a last-bit flip after rounding to float32
+    # both paths keep the reference's Float64 flux and Green-Gauss sums (src/cfd.jl:504-507); the fused kernels take
+    # the Float64 quotients from one reciprocal with Markstein's correction (correctly rounded, physics.cuh)
     assert scaled < 2e-7 and rel < 1e-5, (rel, scaled)
     assert np.array_equal(cf.to_host(), c1)
 
@@ -160,6 +160,42 @@ def test_tile_kernels_match_gather_kernels(get_case, ib, name, mps):
     rel, scaled = _rel_err(out[0][0], out[1][0])
     assert scaled < 1e-6 and rel < 1e-5, (rel, scaled)
     assert np.allclose(out[0][1], out[1][1], rtol=1e-6)
+
+
+@pytest.mark.parametrize("flux", ["hll", "sensor"])
+def test_marching_kernels_bit_identical_to_tile_kernels_and_oracle(get_case, ib, oracle, flux):
+    """3-D 8^3 blocks run the pencil-marching kernel (march.cu), the dedicated general-face kernel and the direct /
+    batched sensor kernels (gen.cu).  Each has an independent predecessor selectable by an environment switch; all
+    variants must give the SAME BITS, and those bits must be the oracle's (integer-exact claim: no tolerance)."""
+    import os
+    c = get_case("sphere3d", 40_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    N = len(c.dom)
+    bf = c.dom.block_faces()
+    kinds = set(np.unique(bf[:, :, 0]).tolist())
+    assert {0, 1, 2, 3} <= kinds, kinds            # box, same-level, coarser and finer contacts are all present
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
+    Q = ib.DeviceArray.from_host(Q0)
+    res = {}
+    for label, env in (("default", {}), ("tile", {"IBX_NO_MARCH": "1"}), ("generic_faces", {"IBX_GEN_OLD": "1"}),
+                       ("tile_sensors", {"IBX_SENSOR_TILES": "1"}), ("one_thread_per_pencil", {"IBX_MARCH_SEG": "1"}),
+                       ("one_stream", {"IBX_ONE_STREAM": "1"})):
+        os.environ.update(env)
+        try:
+            R, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True)
+            ib.residual_euler(c.dom, fl, Q, R, cf, flux=flux)
+            res[label] = (R.to_host(), cf.to_host())
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    for label, (R, cf) in res.items():
+        assert np.array_equal(R, res["default"][0]) and np.array_equal(cf, res["default"][1]), label
+    Ro, co = np.zeros_like(Q0), np.zeros(N, F32)
+    c.odom(E.euler_residual(ofl, flux=flux), Q0.copy(), Ro, co)
+    R, cf = res["default"]
+    assert np.array_equal(R, Ro), (int((R != Ro).sum()), R.size)
+    assert np.array_equal(cf, co)
 
 
 def test_coarse_multigrid_levels_use_tiles(get_case, ib, oracle):

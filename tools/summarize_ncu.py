@@ -16,6 +16,37 @@ def launches(path, out):
         for k, v in agg.items():
             fh.write(f"{k:40s} launches={len(v):3d} avg_ms={sum(v)/len(v)/1e6:9.3f} share={sum(v)/tot*100:5.1f}%\n")
 
+def launches_dram(path, out_txt, out_json, cells, note=""):
+    """Launch list captured with gpu__time_duration.sum + dram__bytes_{read,write}.sum: per-kernel averages, and the
+    DRAM bytes of one residual call (all kernels but the ghost update) as JSON for bench.py's roofline.traffic."""
+    import json
+    rows = list(csv.reader(open(path)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[hdr]; ki = H.index("Kernel Name"); mi = H.index("Metric Name"); vi = H.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi: continue
+        k = r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
+        agg.setdefault(k, collections.defaultdict(list))[r[mi]].append(float(r[vi].replace(",", "")))
+    tot = sum(sum(d["gpu__time_duration.sum"]) for d in agg.values())
+    lines = ["# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 python bench.py --steps 2 --warmup 1",
+             "# (cold-cache, serialised launches: compare SHARES with the live CUDA-event timing of bench.py, not absolutes)"]
+    if note: lines.append("# " + note)
+    lines.append(f"{'kernel':42s} {'n':>3s} {'avg ms':>8s} {'share':>6s} {'DRAM rd MB':>11s} {'DRAM wr MB':>11s}")
+    rd_t = wr_t = t_t = 0.0
+    for k, d in agg.items():
+        t, rd, wr = d["gpu__time_duration.sum"], d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+        lines.append(f"{k:42s} {len(t):3d} {sum(t) / len(t) / 1e6:8.3f} {sum(t) / tot * 100:5.1f}% {sum(rd) / len(rd) / 1e6:11.1f} {sum(wr) / len(wr) / 1e6:11.1f}")
+        if "ghost" not in k:
+            rd_t += sum(rd) / len(rd); wr_t += sum(wr) / len(wr); t_t += sum(t) / len(t)
+    lines.append(f"# one ibx_residual_euler call (everything but the ghost kernels): {t_t / 1e6:.3f} ms serialised, DRAM {rd_t / 1e9:.3f} GB read + "
+                 f"{wr_t / 1e9:.3f} GB written = {(rd_t + wr_t) / cells:.1f} B per cell (algorithmic: 44 B per cell)")
+    open(out_txt, "w").write("\n".join(lines) + "\n")
+    json.dump({"workload": "C4", "cells": cells, "kernel": "ibx_residual_euler (k_prim + sensor kernels + k_gen_faces + k_march_flux)",
+               "dram_bytes_per_launch": rd_t + wr_t, "source": out_txt + " (ncu dram__bytes_read.sum + dram__bytes_write.sum, summed over the kernels of one call)"},
+              open(out_json, "w"), indent=1)
+
+
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -70,4 +101,5 @@ def report(rep, out, cells=None, idx=0):
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "launches": launches(sys.argv[2], sys.argv[3])
+    elif cmd == "launches_dram": launches_dram(sys.argv[2], sys.argv[3], sys.argv[4], int(sys.argv[5]), " ".join(sys.argv[6:]))
     else: report(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4] != '-' else None, int(sys.argv[5]) if len(sys.argv) > 5 else 0)
