@@ -81,6 +81,27 @@ __global__ void k_unpack(float* __restrict__ a, int64_t rows, const int32_t* __r
   }
 }
 
+// all peers in ONE launch (blockIdx.y = peer slot): an exchange is then pack -> grouped send/recv -> unpack, three
+// dependent launches instead of 2 x peers + 1 -- the exchange is latency-bound, not bandwidth-bound (8 MB at 8 ranks)
+constexpr int MAXPEER = 32;
+struct PeerLists {
+  const int32_t* idx[MAXPEER];
+  float* buf[MAXPEER];
+  int64_t n[MAXPEER];
+};
+template <bool PACK>
+__global__ void k_pack_all(float* __restrict__ a, int64_t rows, PeerLists L, int cols) {
+  const int p = blockIdx.y;
+  const int64_t n = L.n[p], tot = n * cols;
+  const int32_t* __restrict__ idx = L.idx[p];
+  float* __restrict__ buf = L.buf[p];
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t % n, col = t / n;
+    if (PACK) buf[t] = a[col * rows + idx[i]];
+    else a[col * rows + idx[i]] = buf[t];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -145,8 +166,25 @@ int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
       CU(cudaMalloc((void**)&S.d_recvbuf[peer], (size_t)need * sizeof(float)));
       S.buf_cap[peer] = need;
     }
-    if (ns) {
+    if (ns && S.nranks > MAXPEER) {
       k_pack<<<grid_for(ns * cols, 256, c->sm_count, 4), 256, 0, c->comm_stream>>>(A.p, A.rows, S.d_send[peer], S.d_sendbuf[peer], ns, cols);
+      LAUNCH_CHECK();
+    }
+  }
+  if (S.nranks <= MAXPEER) {
+    PeerLists L;
+    int np = 0;
+    int64_t nmax = 0;
+    for (int peer = 0; peer < S.nranks; ++peer) {
+      int64_t ns = (int64_t)S.send_local[peer].size();
+      if (!ns) continue;
+      L.idx[np] = S.d_send[peer]; L.buf[np] = S.d_sendbuf[peer]; L.n[np] = ns;
+      nmax = std::max(nmax, ns);
+      ++np;
+    }
+    if (np) {
+      dim3 grid(grid_for(nmax * cols, 256, c->sm_count, 2), np);
+      k_pack_all<true><<<grid, 256, 0, c->comm_stream>>>(A.p, A.rows, L, cols);
       LAUNCH_CHECK();
     }
   }
@@ -159,8 +197,25 @@ int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
   NC(g_nccl.GroupEnd());
   for (int peer = 0; peer < S.nranks; ++peer) {
     int64_t nr = (int64_t)S.recv_local[peer].size();
-    if (nr) {
+    if (nr && S.nranks > MAXPEER) {
       k_unpack<<<grid_for(nr * cols, 256, c->sm_count, 4), 256, 0, c->comm_stream>>>(A.p, A.rows, S.d_recv[peer], S.d_recvbuf[peer], nr, cols);
+      LAUNCH_CHECK();
+    }
+  }
+  if (S.nranks <= MAXPEER) {
+    PeerLists L;
+    int np = 0;
+    int64_t nmax = 0;
+    for (int peer = 0; peer < S.nranks; ++peer) {
+      int64_t nr = (int64_t)S.recv_local[peer].size();
+      if (!nr) continue;
+      L.idx[np] = S.d_recv[peer]; L.buf[np] = S.d_recvbuf[peer]; L.n[np] = nr;
+      nmax = std::max(nmax, nr);
+      ++np;
+    }
+    if (np) {
+      dim3 grid(grid_for(nmax * cols, 256, c->sm_count, 2), np);
+      k_pack_all<false><<<grid, 256, 0, c->comm_stream>>>(A.p, A.rows, L, cols);
       LAUNCH_CHECK();
     }
   }
