@@ -156,9 +156,16 @@ class FlowBC:
         self.P = np.ascontiguousarray(P, dtype=F32)
         self.normal_flow = bool(normal_flow)
 
-    def __call__(self, P, normals):
+    def __call__(self, P, normals, image_distances=None, du_dn=None, transpiration=0.0):
+        """``bc(P, normals; image_distances, du!dn, transpiration)`` (``src/cfd.jl:243-300``)."""
         out = _like(P)
-        call("ibx_flowbc", context(), self.fluid.c, ptr(self.P), len(self.P), int(self.normal_flow), P.h, normals.h, out.h)
+        if image_distances is None and du_dn is None and not isinstance(transpiration, DeviceArray) and transpiration == 0.0:
+            call("ibx_flowbc", context(), self.fluid.c, ptr(self.P), len(self.P), int(self.normal_flow), P.h, normals.h, out.h)
+            return out
+        tr = transpiration if isinstance(transpiration, DeviceArray) else None
+        call("ibx_flowbc_ex", context(), self.fluid.c, ptr(self.P), len(self.P), int(self.normal_flow), P.h, normals.h,
+             image_distances.h if image_distances is not None else 0, du_dn.h if du_dn is not None else 0,
+             tr.h if tr is not None else 0, C.c_float(0.0 if tr is not None else float(transpiration)), out.h)
         return out
 
     def spec(self, boundary_index):

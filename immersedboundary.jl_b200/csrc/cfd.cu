@@ -131,9 +131,10 @@ struct BCParams {
   int normal_flow;
 };
 
-// FlowBC call (src/cfd.jl:243-300), without the optional wall-shear scaling
+// FlowBC call (src/cfd.jl:243-300); the optional wall-shear scaling (:290-296) is applied by k_flowbc_ex
 template <int ND>
-__device__ __forceinline__ void flowbc_point(ibx_fluid f, const BCParams& bc, const float* P, const float* nrm, float* out) {
+__device__ __forceinline__ void flowbc_point(ibx_fluid f, const BCParams& bc, const float* P, const float* nrm, float* out,
+                                             float transpiration = 0.0f) {
   float un;
   if (bc.normal_flow) {
     un = bc.u_inf[0];
@@ -152,7 +153,7 @@ __device__ __forceinline__ void flowbc_point(ibx_fluid f, const BCParams& bc, co
   out[0] = ge * (sup * bc.p_inf + sub * P[0]) + lt * (sup * P[0] + sub * bc.p_inf);
   out[1] = (un > 0.0f ? 1.0f : 0.0f) * bc.T_inf + (un <= 0.0f ? 1.0f : 0.0f) * P[1];
   if (bc.normal_flow) {
-    float corr = un - cur + 0.0f;  // + transpiration (0)
+    float corr = un - cur + transpiration;
 #pragma unroll
     for (int d = 0; d < ND; ++d) out[2 + d] = P[2 + d] + nrm[d] * corr;
   } else {
@@ -172,6 +173,34 @@ __global__ void k_flowbc(ibx_fluid f, BCParams bc, const float* __restrict__ P, 
 #pragma unroll
     for (int d = 0; d < ND; ++d) nn[d] = nrm[(int64_t)d * n + i];
     flowbc_point<ND>(f, bc, p, nn, o);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[(int64_t)v * n + i] = o[v];
+  }
+}
+
+// FlowBC with the keyword arguments of src/cfd.jl:245-249: transpiration (scalar or per point) and, when du!dn and
+// image_distances are given, the wall-shear scaling ub *= (V - du!dn * d) / V, V = |ub| + eps (:290-296)
+template <int ND>
+__global__ void k_flowbc_ex(ibx_fluid f, BCParams bc, const float* __restrict__ P, const float* __restrict__ nrm,
+                            const float* __restrict__ dist, const float* __restrict__ dudn, const float* __restrict__ transp,
+                            float transp_scalar, float* __restrict__ out, int64_t n) {
+  constexpr int NV = 2 + ND;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[NV], nn[ND], o[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) p[v] = P[(int64_t)v * n + i];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) nn[d] = nrm[(int64_t)d * n + i];
+    flowbc_point<ND>(f, bc, p, nn, o, transp ? transp[i] : transp_scalar);
+    if (dudn) {
+      float s = o[2] * o[2];
+#pragma unroll
+      for (int d = 1; d < ND; ++d) s = s + o[2 + d] * o[2 + d];
+      const float V = sqrtf(s) + 1.1920929e-7f;
+      const float k = (V - dudn[i] * dist[i]) / V;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) o[2 + d] = o[2 + d] * k;
+    }
 #pragma unroll
     for (int v = 0; v < NV; ++v) out[(int64_t)v * n + i] = o[v];
   }
@@ -335,6 +364,47 @@ int ibx_flowbc(ibx_ctx* c, ibx_fluid f, const float* Pinf, int n_pinf, int norma
   bc.normal_flow = normal_flow;
   if (nd == 2) k_flowbc<2><<<GRID(A.rows)>>>(f, bc, A.p, N.p, O.p, A.rows);
   else k_flowbc<3><<<GRID(A.rows)>>>(f, bc, A.p, N.p, O.p, A.rows);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
+
+int ibx_flowbc_ex(ibx_ctx* c, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow, ibx_array P, ibx_array normals,
+                  ibx_array image_distances, ibx_array du_dn, ibx_array transpiration, float transpiration_scalar, ibx_array out) {
+  CHECK_CTX(c);
+  GET_ARR(A, P);
+  GET_ARR(N, normals);
+  GET_ARR(O, out);
+  SHAPE(A.rows == N.rows && A.rows == O.rows && A.cols == O.cols && (A.cols == 4 || A.cols == 5) && N.cols == A.cols - 2,
+        "P, out N x (2 + nd); normals N x nd");
+  int nd = (int)A.cols - 2;
+  if (normal_flow) {
+    if (n_pinf != 3)  // the reference's @assert (src/cfd.jl:254)
+      return fail(IBX_ERR_ARG, "Only 3 parcels in P (p, T and normal flow) allowed for normal_flow = true BC");
+  } else if (n_pinf != 2 + nd) {
+    return fail(IBX_ERR_ARG, "ibx_flowbc_ex: Pinf must hold p, T and nd velocity components");
+  }
+  if ((du_dn == 0) != (image_distances == 0))  // the reference's error (src/cfd.jl:286-288)
+    return fail(IBX_ERR_ARG, "du!dn and image_distances must be passed together for BC imposition");
+  const float *dist = nullptr, *dn = nullptr, *tr = nullptr;
+  if (du_dn) {
+    GET_ARR(Dd, image_distances);
+    GET_ARR(Dn, du_dn);
+    SHAPE(Dd.rows * Dd.cols == A.rows && Dn.rows * Dn.cols == A.rows, "image_distances and du!dn must have one entry per point");
+    dist = Dd.p;
+    dn = Dn.p;
+  }
+  if (transpiration) {
+    GET_ARR(Tt, transpiration);
+    SHAPE(Tt.rows * Tt.cols == A.rows, "transpiration must have one entry per point");
+    tr = Tt.p;
+  }
+  BCParams bc{};
+  bc.p_inf = Pinf[0];
+  bc.T_inf = Pinf[1];
+  for (int k = 0; k < n_pinf - 2; ++k) bc.u_inf[k] = Pinf[2 + k];
+  bc.normal_flow = normal_flow;
+  if (nd == 2) k_flowbc_ex<2><<<GRID(A.rows)>>>(f, bc, A.p, N.p, dist, dn, tr, transpiration_scalar, O.p, A.rows);
+  else k_flowbc_ex<3><<<GRID(A.rows)>>>(f, bc, A.p, N.p, dist, dn, tr, transpiration_scalar, O.p, A.rows);
   LAUNCH_CHECK();
   return IBX_OK;
 }

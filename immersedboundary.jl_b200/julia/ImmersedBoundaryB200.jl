@@ -353,10 +353,13 @@ struct Fluid; R::Float32; γ::Float32; end
 Fluid(; R::Real = 283.0f0, γ::Real = 1.4f0, kwargs...) = Fluid(R, γ)
 struct FlowBC; fluid::Fluid; P::Vector{Float32}; normal_flow::Bool; end
 FlowBC(fluid::Fluid, P::AbstractVector; normal_flow::Bool = false) = FlowBC(fluid, Float32.(P), normal_flow)
-function (bc::FlowBC)(P::IBXArray, normals::IBXArray)
+function (bc::FlowBC)(P::IBXArray, normals::IBXArray; image_distances::Union{Nothing, IBXArray} = nothing,
+                      du!dn::Union{Nothing, IBXArray} = nothing, transpiration::Union{Real, IBXArray} = 0.0f0)
     out = similar(P)
-    check(ccall((:ibx_flowbc, libibx), Cint, (Ptr{Cvoid}, Fluid, Ptr{Float32}, Cint, Cint, Int64, Int64, Int64),
-                context(), bc.fluid, bc.P, length(bc.P), bc.normal_flow, P.h, normals.h, out.h)); out
+    h(x) = x isa IBXArray ? x.h : Int64(0)
+    check(ccall((:ibx_flowbc_ex, libibx), Cint, (Ptr{Cvoid}, Fluid, Ptr{Float32}, Cint, Cint, Int64, Int64, Int64, Int64, Int64, Cfloat, Int64),
+                context(), bc.fluid, bc.P, length(bc.P), bc.normal_flow, P.h, normals.h, h(image_distances), h(du!dn), h(transpiration),
+                transpiration isa Real ? Float32(transpiration) : 0.0f0, out.h)); out
 end
 for (jn, cn) in ((:state2primitive, :ibx_state2primitive), (:primitive2state, :ibx_primitive2state), (:speed_of_sound, :ibx_speed_of_sound))
     @eval function $jn(fluid::Fluid, A::IBXArray)

@@ -248,6 +248,11 @@ int ibx_inviscid_fluxes_sensor(ibx_ctx* c, ibx_fluid f, ibx_array PL, ibx_array 
 int ibx_flowbc(ibx_ctx* c, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow, ibx_array P,
                ibx_array normals, ibx_array out);
 
+/* the same call with the keyword arguments of src/cfd.jl:245-249: transpiration (per-point array, or 0 and the scalar)
+ * and the wall-shear scaling of :290-296 when image_distances and du_dn are both given (both 0: none) */
+int ibx_flowbc_ex(ibx_ctx* c, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow, ibx_array P, ibx_array normals,
+                  ibx_array image_distances, ibx_array du_dn, ibx_array transpiration, float transpiration_scalar, ibx_array out);
+
 /* ------------------------------------------------------------------ pointwise closures around the residual */
 /* Sutherland / conductivity-polynomial constants of Fluid (src/cfd.jl:14-53): mu_ref, T_ref, S, k[0..nk-1] */
 typedef struct ibx_transport { float mu_ref, T_ref, S; int nk; float k[4]; } ibx_transport;

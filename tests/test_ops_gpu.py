@@ -93,6 +93,17 @@ def test_cfd_kernels(ib, oracle):
             ob = cfd.FlowBC(ofl, Pinf, normal_flow=nf)(P, nrm)
             db = ib.FlowBC(fl, Pinf, normal_flow=nf)(dP, dn).to_host()
             assert np.array_equal(db, ob)
+            # keyword arguments of src/cfd.jl:245-249: transpiration and the wall-shear scaling
+            dist, dudn = _rand(n, seed=11, lo=1e-3, hi=1e-2), _rand(n, seed=12, lo=0, hi=5e3)
+            tr = _rand(n, seed=13, lo=-1, hi=1)
+            ob = cfd.FlowBC(ofl, Pinf, normal_flow=nf)(P, nrm, image_distances=dist, du_dn=dudn, transpiration=tr)
+            db = ib.FlowBC(fl, Pinf, normal_flow=nf)(dP, dn, image_distances=ib.DeviceArray.from_host(dist),
+                                                     du_dn=ib.DeviceArray.from_host(dudn), transpiration=ib.DeviceArray.from_host(tr)).to_host()
+            assert np.allclose(db, ob, rtol=2e-7, atol=0) and np.array_equal(db[:, :2], ob[:, :2])
+            ob = cfd.FlowBC(ofl, Pinf, normal_flow=nf)(P, nrm, transpiration=F32(0.25))
+            assert np.array_equal(ib.FlowBC(fl, Pinf, normal_flow=nf)(dP, dn, transpiration=0.25).to_host(), ob)
+    with pytest.raises(ib.IbxError, match="passed together"):
+        ib.FlowBC(fl, Pinf, normal_flow=True)(dP, dn, du_dn=dn.col(0))
     with pytest.raises(ib.IbxError, match="Only 3 parcels"):
         ib.FlowBC(fl, np.zeros(4, F32), normal_flow=True)(dP, dn)
 
