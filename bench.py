@@ -96,30 +96,60 @@ def measured_peak_gbs():
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference(cells_target, steps, warmup):
-    """The restated reference path (oracle: array-at-a-time operators, one task per partition like
-    ThreadTools.tmap) on a BOUNDED sample: the same sphere-octree recipe at a coarser size."""
+def cpu_reference(ball_radius, steps, warmup):
+    """The restated reference path on the host cores, on a BOUNDED sample: the same sphere-octree recipe at a coarser
+    size.  Compiled C + OpenMP restatement (oracle/cpu_ref.c: one task per partition like ThreadTools.tmap, gather ->
+    array-at-a-time operators with temporaries -> scatter; bit-identical to the NumPy oracle,
+    tests/test_oracle_cpu_ref.py); the NumPy oracle itself if no C compiler is available."""
     import oracle
     from oracle import cfd as ocfd, euler as oeuler
     from immersedboundary_jl_b200 import synthetic
-    OM = oracle.mesher
     cores = os.cpu_count() or 1
-    h = F32(0.25)
     fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
-    msh = OM.Mesh([-16, -16, -16], [32, 32, 32], ("wall", OM.AnalyticSphere([0, 0, 0], 0.5), h),
-                  refinement_regions=[(OM.Ball([0, 0, 0], cells_target), h)])
-    dom = oracle.domain.Domain(msh, max_partition_size=max(4096, len(msh) // max(cores, 1) + 1), hypercube_families=fams)
     fl = ocfd.Fluid()
     a = np.sqrt(1.4 * 283.0 * 288.15)
     Pinf = np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)
     bcs = [("wall", ocfd.FlowBC(fl, Pinf[:3] * np.array([1, 1, 0], F32), normal_flow=True)), ("farfield", ocfd.FlowBC(fl, Pinf))]
-    Q = synthetic.primitive2state_host(synthetic.euler_state(dom.centers))
-    R, cf = np.zeros_like(Q), np.zeros(len(Q), F32)
-    res = oeuler.euler_residual(fl)
+    try:
+        from oracle import cpu_ref
+        cpu_ref.build()
+        compiled = True
+    except Exception:
+        compiled = False
+    if compiled:
+        # tables from the product's HOST-side C++ builder (no GPU involved; identical to the oracle's own tables,
+        # tests/test_builder_parity.py) -- the NumPy builder is too slow for a multi-million-cell sample
+        import immersedboundary_jl_b200 as ib
+        h = F32(0.125)
+        msh = ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", ib.Sphere([0, 0, 0], 0.5), h),
+                      refinement_regions=[(ib.Ball([0, 0, 0], 2.0 * ball_radius), h)])
+        n = len(msh)
+        dom = ib.Domain(msh, max_partition_size=max(4096, n // (4 * cores) + 1), hypercube_families=fams, build_partitions=True,
+                        build_surfaces=False, upload=False)
+        ref = cpu_ref.CpuRef.from_builder(dom)
+        Q = np.asfortranarray(synthetic.primitive2state_host(synthetic.euler_state(dom.cells()[0])))
+        R, cf = np.zeros((n, 5), F32, order="F"), np.zeros(n, F32)
+        nparts = len(dom.partitions)
 
-    def step():
-        oeuler.euler_ghost_update(dom, fl, Q, bcs)
-        dom(res, Q, R, cf, n_threads=cores)
+        def step():
+            ref.ghost_update(fl, Q, bcs, cores)
+            ref.residual(fl, Q, R, cf, cores)
+        what = "compiled C + OpenMP restatement of the reference operators (oracle/cpu_ref.c)"
+    else:
+        OM = oracle.mesher
+        h = F32(0.25)
+        msh = OM.Mesh([-16, -16, -16], [32, 32, 32], ("wall", OM.AnalyticSphere([0, 0, 0], 0.5), h),
+                      refinement_regions=[(OM.Ball([0, 0, 0], ball_radius), h)])
+        dom = oracle.domain.Domain(msh, max_partition_size=max(4096, len(msh) // max(cores, 1) + 1), hypercube_families=fams)
+        Q = synthetic.primitive2state_host(synthetic.euler_state(dom.centers))
+        R, cf = np.zeros_like(Q), np.zeros(len(Q), F32)
+        res = oeuler.euler_residual(fl)
+        n, nparts = len(Q), len(dom.partitions)
+
+        def step():
+            oeuler.euler_ghost_update(dom, fl, Q, bcs)
+            dom(res, Q, R, cf, n_threads=cores)
+        what = "NumPy restatement of the reference operators"
 
     for _ in range(warmup):
         step()
@@ -127,20 +157,20 @@ def cpu_reference(cells_target, steps, warmup):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": len(Q) * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-            "sample": f"NumPy restatement of the reference operators (Julia cannot run here), same sphere-octree recipe at "
-                      f"h={float(h)} -> {len(Q)} cells in {len(dom.partitions)} partitions, {steps} evaluations, "
-                      f"{cores} threads (one task per partition, like tmap)",
-            "ms_per_step": dt / steps * 1e3, "cells": len(Q)}
+    return {"value": n * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"{what} (Julia cannot run here), same sphere-octree recipe at h={float(h)} -> {n} cells in "
+                      f"{nparts} partitions, {steps} evaluations (ghost update + residual), {cores} threads "
+                      f"(one task per partition, like tmap)",
+            "ms_per_step": dt / steps * 1e3, "cells": n}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(1.5, max(1, min(args.steps, 5)), min(args.warmup, 1))
+    r = cpu_reference(2.5, max(1, min(args.steps, 20)), min(args.warmup, 1))
     line = {"impl": "reference", "metric": "cell-updates/s (Euler residual+IB)", "value": r["value"], "unit": "cell-updates/s",
-            "n_gpus": args.gpus, "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": max(1, min(args.steps, 20)), "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "3-D sphere octree Euler (HLL + MUSCL + JST) + IB ghost update, bounded CPU sample",
                        "cells": r["cells"]},
@@ -334,7 +364,7 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(1.5, 3, 1)
+        r = cpu_reference(2.5, 10, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
         "metric": "cell-updates/s (Euler residual+IB)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
