@@ -62,6 +62,13 @@ class Case:
             ofeat = OM.DistanceField(OM.feature_regions(ostl, radius=0.05))
             self.omsh = OM.Mesh(np.array([-25, -25], F32), np.array([50, 50], F32), ("wall", ostl, F32(1e-2)),
                                 refinement_regions=[(ofeat, F32(5e-3))])
+        elif name == "sphere3d_np2":
+            # root box widths that are NOT powers of two: the kernels' exact power-of-two shortcuts must switch off
+            self.fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+            self.msh = M.Mesh([-1.5, -1.5, -1.5], [3, 3, 3], ("wall", M.Sphere([0, 0, 0], 0.4), F32(0.05)),
+                              refinement_regions=[(M.Ball([0, 0, 0], 0.7), F32(0.1))])
+            self.omsh = OM.Mesh([-1.5, -1.5, -1.5], [3, 3, 3], ("wall", OM.AnalyticSphere([0, 0, 0], 0.4), F32(0.05)),
+                                refinement_regions=[(OM.Ball([0, 0, 0], 0.7), F32(0.1))])
         elif name in ("sphere3d", "sphere3d_stl"):
             self.fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
             if name == "sphere3d":

@@ -198,6 +198,27 @@ def test_marching_kernels_bit_identical_to_tile_kernels_and_oracle(get_case, ib,
     assert np.array_equal(cf, co)
 
 
+def test_non_power_of_two_spacings_3d(get_case, ib, oracle):
+    """A 3-D mesh whose cell widths are not powers of two: the exact shortcuts (x / h == x * (1 / h), the marching
+    kernel) are off, the true divisions are on, and the result is still the oracle's bit for bit."""
+    c = get_case("sphere3d_np2", 40_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    N = len(c.dom)
+    h = c.dom.cells()[1]
+    assert not np.all(np.log2(h) == np.round(np.log2(h)))
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
+    Q = ib.DeviceArray.from_host(Q0)
+    for flux in ("hll", "sensor"):
+        R, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True)
+        ib.residual_euler(c.dom, fl, Q, R, cf, flux=flux)
+        Ro, co = np.zeros_like(Q0), np.zeros(N, F32)
+        c.odom(E.euler_residual(ofl, flux=flux), Q0.copy(), Ro, co)
+        Rg = R.to_host()
+        assert np.array_equal(Rg, Ro), (flux, int((Rg != Ro).sum()), Rg.size)
+        assert np.array_equal(cf.to_host(), co)
+
+
 def test_coarse_multigrid_levels_use_tiles(get_case, ib, oracle):
     """block_size 4 and 2 (the multigrid levels of src/ImmersedBoundary.jl:1355-1407) through the same kernels."""
     c = get_case("sphere3d", 40_000, upload=True)
