@@ -61,3 +61,51 @@ def test_rae2822_march_lift_and_drag(get_case, ib, oracle):
     (cl, cd), (clo, cdo) = _coefficients(F), _coefficients(Fo)
     assert abs(cl - clo) < 1e-4 and abs(cd - cdo) < 1e-4, (cl, clo, cd, cdo)
     assert abs(cl) > 1e-3                                        # the incidence produces lift within the first steps
+
+
+def test_rae2822_fas_multigrid_cycle(get_case, ib, oracle):
+    """C3 "with mgrid multigrid": one FAS V-cycle (src/solver.jl:39-91) over the block_size 8 -> 4 -> 2 hierarchy of
+    multigrid(dom) (src/ImmersedBoundary.jl:1355-1407) with the Euler residual + IB ghost update on every level,
+    entirely on device arrays (restriction / prolongation through the IDW transfer accumulators, clamped update,
+    norms), next to the oracle running the same cycle."""
+    c = get_case("rae2822", 10_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    a_inf = np.sqrt(1.4 * 283.0 * 288.15)
+    d = ib.streamwise_direction(ALPHA)
+    Pinf = np.array([101325.0, 288.15, MACH * a_inf * d[0], MACH * a_inf * d[1]], F32)
+    wall = np.array([101325.0, 288.15, 0.0], F32)
+    bcs = [("wall", ib.FlowBC(fl, wall, normal_flow=True)), ("farfield", ib.FlowBC(fl, Pinf))]
+    obcs = [("wall", cfd.FlowBC(ofl, wall, normal_flow=True)), ("farfield", cfd.FlowBC(ofl, Pinf))]
+    cd, pro, coa = ib.multigrid(c.dom)
+    ocd, opro, ocoa = oracle.domain.multigrid(c.odom)
+    doms, odoms = [c.dom] + cd, [c.odom] + ocd
+    assert [len(x) for x in doms] == [len(x.centers) for x in odoms] and len(doms) == 4
+    doms, odoms, coa, pro, ocoa, opro = doms[:3], odoms[:3], coa[:2], pro[:2], ocoa[:2], opro[:2]
+
+    def f(l, Q):
+        Qg = Q.copy()
+        ib.ghost_update_euler(doms[l], fl, Qg, bcs)
+        R, cf = ib.DeviceArray(Q.rows, 4, False), ib.DeviceArray(Q.rows, 1, True)
+        ib.residual_euler(doms[l], fl, Qg, R, cf)
+        return R * (float(CFL) / cf), 1.0
+
+    def fo(l, Q):
+        Qg = Q.copy()
+        E.euler_ghost_update(odoms[l], ofl, Qg, obcs)
+        R, cf = np.zeros_like(Q), np.zeros(len(Q), F32)
+        odoms[l](E.euler_residual(ofl), Qg, R, cf)
+        return R * (CFL / cf)[:, None], F32(1.0)
+
+    Q0 = ib.synthetic.primitive2state_host(np.tile(Pinf, (len(c.dom), 1)))
+    Q = ib.DeviceArray.from_host(Q0)
+    ratio = ib.FAS(f, Q, coa, pro, n_iter=3, rtol=1e-6)
+    Qo = Q0.copy()
+    oratio = oracle.solver.FAS(fo, Qo, ocoa, opro, n_iter=3, rtol=F32(1e-6))
+    Qh = Q.to_host()
+    qs = np.abs(Qo).max(axis=0)
+    assert np.isfinite(Qh).all() and np.abs(Qh - Q0).max() > 0
+    # the transfer and ghost-interpolation weights agree to ~1e-6 (float32 SVD vs double Jacobi); a residual amplifies a
+    # relative change of its input by ~1e2 (DESIGN.md 4.1), and the cycle chains ~12 evaluations over three levels
+    assert (np.abs(Qh - Qo) / qs).max() < 5e-4, (np.abs(Qh - Qo) / qs).max()
+    assert abs(float(ratio) - float(oratio)) < 1e-3 * max(float(oratio), 1e-6), (ratio, oratio)
