@@ -42,7 +42,8 @@ struct MarchCfg {
 };
 
 // HYB 0: regular blocks (all six neighbours same level).  1: irregular, no finer neighbour.  2: with finer neighbours.
-template <int FLUX, int SEG, int HYB>
+// X2: the stencil advance and MUSCL on packed FP32 pairs (two variables per FADD2 / FMUL2), physics.cuh
+template <int FLUX, int SEG, int HYB, bool X2>
 __global__ void __launch_bounds__(MarchCfg<SEG>::NT, 5)
 k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
              ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, float* __restrict__ R,
@@ -53,6 +54,8 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
   constexpr int NX = HYB == 2 ? 2 * FACE * 4 : 0;   // scratch slots of the fine faces (HybCfg::NX)
   constexpr int NSL = 4 * FACE + NX;                // scratch slots per (block, dimension)
   using FT = typename std::conditional<FLUX == 0, double, float>::type;
+  using S = typename std::conditional<X2, P2, float>::type;   // one register of the marching state
+  constexpr int NR = X2 ? (NV + 1) / 2 : NV;                   // registers per cell
   extern __shared__ float smem_f[];
   float* sP = smem_f;                 // [NV][FS] primitives, then [DS] sensor
   float* sD = sP + NV * FS;
@@ -156,39 +159,39 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
     const int64_t gbase = ((int64_t)blockIdx.x * ND + d) * NSL;
     // ---- stencil of the first face of this thread's segment: owner = cell f0 - 1, neighbour = cell f0
     const int sm = posP(f0 - 2), so = posP(f0 - 1), sn = posP(f0);
-    float uo[NV], un[NV], fc[NV], dfo[NV];   // dfo = fl(fc - fm): the owner's gradient along d times hd
+    const S half = vsplat<S>(0.5f);
+    S uo[NR], un[NR], fc[NR], dfo[NR];   // dfo = fl(fc - fm): the owner's gradient along d times hd
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float um = sP[v * FS + sm];
-      uo[v] = sP[v * FS + so];
-      un[v] = sP[v * FS + sn];
-      float fm = (um + uo[v]) * 0.5f;
-      fc[v] = (uo[v] + un[v]) * 0.5f;
-      dfo[v] = fc[v] - fm;
+    for (int k = 0; k < NR; ++k) {
+      const S um = vload<S, NV>(sP, k, FS, sm);
+      uo[k] = vload<S, NV>(sP, k, FS, so);
+      un[k] = vload<S, NV>(sP, k, FS, sn);
+      const S fm = vmul(vadd(um, uo[k]), half);
+      fc[k] = vmul(vadd(uo[k], un[k]), half);
+      dfo[k] = vsub(fc[k], fm);
     }
     float Do = sD[posD(f0 - 1)], Dn = sD[posD(f0)];
-    float ao = sqrt_rn_inrange(gr * clampT(uo[1])), an = sqrt_rn_inrange(gr * clampT(un[1]));
+    float ao = sqrt_rn_inrange(gr * clampT(vget(uo, 1))), an = sqrt_rn_inrange(gr * clampT(vget(un, 1)));
     int rl = own0 + (f0 - 1) * ss;                    // running-residual slot / block-local id of the owner cell
     int l = (f0 - 1) * ls + t1 * l1 + t2 * l2;
     FT Fa[NV], Fb[NV];
     float ca = 0.0f, cb = 0.0f;
     // one face: advance the stencil, flux (or scratch), and -- when UPDATE -- the Green-Gauss update of the owner cell
-    auto face = [&](int f, auto update, float (&qo)[NV], float (&qn)[NV], float (&qp)[NV], float (&fcc)[NV], float (&fpp)[NV],
-                    float (&dfc)[NV], float (&dfp)[NV], FT (&Fl)[NV], FT (&Fh)[NV], float& cl, float& ch, float& D0, float& D1,
-                    float& D2, float& a0, float& a1) {
+    auto face = [&](int f, auto update, auto& qo, auto& qn, auto& qp, auto& fcc, auto& fpp, auto& dfc, auto& dfp, auto& Fl, auto& Fh,
+                    float& cl, float& ch, float& D0, float& D1, float& D2, float& a0, float& a1) {   // (S[NR] x 7, FT[NV] x 2)
       constexpr bool UPDATE = decltype(update)::value;
       const int s = posP(f + 1);
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        qp[v] = sP[v * FS + s];
-        fpp[v] = (qn[v] + qp[v]) * 0.5f;
-        dfp[v] = fpp[v] - fcc[v];
+      for (int k = 0; k < NR; ++k) {
+        qp[k] = vload<S, NV>(sP, k, FS, s);
+        fpp[k] = vmul(vadd(qn[k], qp[k]), half);
+        dfp[k] = vsub(fpp[k], fcc[k]);
       }
       D2 = sD[posD(f + 1)];
       const bool take = HYB != 0 && ((irr_lo && f <= 1) || (irr_hi && f >= BS - 1));
       if (!take) {
         float pl[NV], pr[NV];
-        muscl_face_p2<NV>(qo, qn, fcc, dfc, dfp, D0, D1, pl, pr);
+        muscl_face_p2v<S, NV, NR>(qo, qn, fcc, dfc, dfp, D0, D1, pl, pr);
         if (FLUX == 0) {
           double Fd[NV];
           hll_flux<ND, true>(fl, pl, pr, d, Fd);
@@ -200,7 +203,8 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
 #pragma unroll
           for (int v = 0; v < NV; ++v) Fh[v] = (FT)Ff[v];
         }
-        ch = fabsf((pick<ND>(qo + 2, d) + pick<ND>(qn + 2, d)) * 0.5f) + (a0 + a1) * 0.5f;
+        const float vo[ND] = {vget(qo, 2), vget(qo, 3), vget(qo, 4)}, vn[ND] = {vget(qn, 2), vget(qn, 3), vget(qn, 4)};
+        ch = fabsf((pick<ND>(vo, d) + pick<ND>(vn, d)) * 0.5f) + (a0 + a1) * 0.5f;
       } else if (HYB == 2 && ((f == 0 && fine_lo) || (f == BS && fine_hi))) {
         // block face towards finer neighbours: mean of its four fine faces, products first, in list order
         const int side = f == 0 ? 0 : 1;
@@ -243,12 +247,13 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
         if (d == ND - 1) cfl[cell0 + l] = cnew;
         else sCf[rl] = cnew;
       }
-      a0 = sqrt_rn_inrange(gr * clampT(qp[1]));   // becomes the neighbour's speed of sound two faces on
+      a0 = sqrt_rn_inrange(gr * clampT(vget(qp, 1)));   // becomes the neighbour's speed of sound two faces on
       rl += ss; l += ls;
     };
     // register roles rotate with period 6 (3 for the cell values, 2 for everything else): the loop is unrolled by hand
     // over one period so that no state is ever copied
-    float up[NV], fp[NV], dfn[NV], Dp;
+    S up[NR], fp[NR], dfn[NR];
+    float Dp;
     std::true_type U;
     std::false_type NU;
     // f0: flux only
@@ -276,27 +281,32 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
   }
 }
 
-template <int FLUX, int SEG, int HYB>
+template <int FLUX, int SEG, int HYB, bool X2>
 int launch_march(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
                  float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
   using C = MarchCfg<SEG>;
   static bool attr = false;
   if (!attr) {
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  k_march_flux<FLUX, SEG, HYB><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  k_march_flux<FLUX, SEG, HYB, X2><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
 }
 
 template <int FLUX, int SEG>
-int launch_march_h(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, const float* P,
+int launch_march_h(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, bool x2, ibx_fluid f, const float* P,
                    const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
-  if (hyb == 0) return launch_march<FLUX, SEG, 0>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  if (hyb == 1) return launch_march<FLUX, SEG, 1>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  return launch_march<FLUX, SEG, 2>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (x2) {
+    if (hyb == 0) return launch_march<FLUX, SEG, 0, true>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+    if (hyb == 1) return launch_march<FLUX, SEG, 1, true>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+    return launch_march<FLUX, SEG, 2, true>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  }
+  if (hyb == 0) return launch_march<FLUX, SEG, 0, false>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (hyb == 1) return launch_march<FLUX, SEG, 1, false>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  return launch_march<FLUX, SEG, 2, false>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
 }
 
 }  // namespace
@@ -312,12 +322,13 @@ int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, in
   if (n == 0) return IBX_OK;
   const char* e = getenv("IBX_MARCH_SEG");   // threads per pencil (1 or 2); 2 measured faster on C4
   const int seg = e && atoi(e) == 1 ? 1 : 2;
+  const bool x2 = getenv("IBX_MARCH_SCALAR") == nullptr;   // IBX_MARCH_SCALAR=1: scalar FADD / FMUL instead of the packed pairs
   if (flux_kind == 0) {
-    if (seg == 1) return launch_march_h<0, 1>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
-    return launch_march_h<0, 2>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
+    if (seg == 1) return launch_march_h<0, 1>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
+    return launch_march_h<0, 2>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
   }
-  if (seg == 1) return launch_march_h<1, 1>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
-  return launch_march_h<1, 2>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st);
+  if (seg == 1) return launch_march_h<1, 1>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
+  return launch_march_h<1, 2>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
 }
 
 }  // namespace ibx
