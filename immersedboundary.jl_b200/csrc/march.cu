@@ -43,7 +43,10 @@ struct MarchCfg {
 
 // HYB 0: regular blocks (all six neighbours same level).  1: irregular, no finer neighbour.  2: with finer neighbours.
 // X2: the stencil advance and MUSCL on packed FP32 pairs (two variables per FADD2 / FMUL2), physics.cuh
-template <int FLUX, int SEG, int HYB, bool X2>
+// SHARE (two threads per pencil): the middle face of a pencil is evaluated once -- the upper thread skips the flux of its
+// first face, hands the flux of its second face to the lower thread through the pencil's (by then dead) low-halo slots,
+// and the lower thread updates the cell between them; producer / consumer named barriers, no CTA-wide wait.
+template <int FLUX, int SEG, int HYB, bool X2, bool SHARE>
 __global__ void __launch_bounds__(MarchCfg<SEG>::NT, 5)
 k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
              ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, float* __restrict__ R,
@@ -177,9 +180,27 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
     FT Fa[NV], Fb[NV];
     float ca = 0.0f, cb = 0.0f;
     // one face: advance the stencil, flux (or scratch), and -- when UPDATE -- the Green-Gauss update of the owner cell
-    auto face = [&](int f, auto update, auto& qo, auto& qn, auto& qp, auto& fcc, auto& fpp, auto& dfc, auto& dfp, auto& Fl, auto& Fh,
-                    float& cl, float& ch, float& D0, float& D1, float& D2, float& a0, float& a1) {   // (S[NR] x 7, FT[NV] x 2)
+    // Green-Gauss update of the cell at (rl, l) from the fluxes of its low (Fl, cl) and high (Fh, ch) faces along d
+    auto cell_update = [&](auto& Fl, auto& Fh, float cl, float ch) {
+      const float cprev = d == 0 ? 0.0f : sCf[rl];
+      const float cnew = cprev + (ch + cl) * inv_hd;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float prev = d == 0 ? 0.0f : sR[v * RS + rl];
+        float r;
+        if (FLUX == 0) r = (float)((double)prev - ((double)Fh[v] - (double)Fl[v]) * inv_hd_d);
+        else r = prev - ((float)Fh[v] - (float)Fl[v]) * inv_hd;
+        if (d == ND - 1) R[(int64_t)v * N + cell0 + l] = r;
+        else sR[v * RS + rl] = r;
+      }
+      if (d == ND - 1) cfl[cell0 + l] = cnew;
+      else sCf[rl] = cnew;
+    };
+    // mode 0: plain.  SHARE, upper thread: mode 1 = advance only (no flux), mode 2 = hand the flux over instead of updating
+    auto face = [&](int f, auto update, const int mode, auto& qo, auto& qn, auto& qp, auto& fcc, auto& fpp, auto& dfc, auto& dfp,
+                    auto& Fl, auto& Fh, float& cl, float& ch, float& D0, float& D1, float& D2, float& a0, float& a1) {   // (S[NR] x 7, FT[NV] x 2)
       constexpr bool UPDATE = decltype(update)::value;
+      const bool upper = SHARE && seg == 1;
       const int s = posP(f + 1);
 #pragma unroll
       for (int k = 0; k < NR; ++k) {
@@ -189,7 +210,9 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
       }
       D2 = sD[posD(f + 1)];
       const bool take = HYB != 0 && ((irr_lo && f <= 1) || (irr_hi && f >= BS - 1));
-      if (!take) {
+      if (mode == 1 && upper) {
+        // the lower thread of this pencil evaluates this face
+      } else if (!take) {
         float pl[NV], pr[NV];
         muscl_face_p2v<S, NV, NR>(qo, qn, fcc, dfc, dfp, D0, D1, pl, pr);
         if (FLUX == 0) {
@@ -232,20 +255,25 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
         ch = GC[sid];
       }
       if (UPDATE) {
-        // the owner cell (f - 1) now has both of its faces along d
-        const float cprev = d == 0 ? 0.0f : sCf[rl];
-        const float cnew = cprev + (ch + cl) * inv_hd;
+        if (mode == 2 && upper) {
+          // hand (Fh, ch) to the lower thread: the pencil's low-halo slots were last read by its initialisation
+          asm volatile("bar.sync 2, %0;" ::"n"(NT));
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const float prev = d == 0 ? 0.0f : sR[v * RS + rl];
-          float r;
-          if (FLUX == 0) r = (float)((double)prev - ((double)Fh[v] - (double)Fl[v]) * inv_hd_d);
-          else r = prev - ((float)Fh[v] - (float)Fl[v]) * inv_hd;
-          if (d == ND - 1) R[(int64_t)v * N + cell0 + l] = r;
-          else sR[v * RS + rl] = r;
+          for (int v = 0; v < NV; ++v) {
+            if (FLUX == 0) {
+              const unsigned long long b = (unsigned long long)__double_as_longlong((double)Fh[v]);
+              sP[v * FS + hP] = __uint_as_float((unsigned)b);
+              sP[v * FS + hP + FACE] = __uint_as_float((unsigned)(b >> 32));
+            } else {
+              sP[v * FS + hP] = (float)Fh[v];
+            }
+          }
+          sD[hD] = ch;
+          __threadfence_block();
+          asm volatile("bar.arrive 1, %0;" ::"n"(NT));
+        } else {
+          cell_update(Fl, Fh, cl, ch);   // the owner cell (f - 1) now has both of its faces along d
         }
-        if (d == ND - 1) cfl[cell0 + l] = cnew;
-        else sCf[rl] = cnew;
       }
       a0 = sqrt_rn_inrange(gr * clampT(vget(qp, 1)));   // becomes the neighbour's speed of sound two faces on
       rl += ss; l += ls;
@@ -257,56 +285,77 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
     std::true_type U;
     std::false_type NU;
     // f0: flux only
-    face(f0, NU, uo, un, up, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Do, Dn, Dp, ao, an);
+    if (SHARE && seg == 0) asm volatile("bar.arrive 2, %0;" ::"n"(NT));   // this pencil's low-halo slots are free now
+    face(f0, NU, SHARE ? 1 : 0, uo, un, up, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Do, Dn, Dp, ao, an);
     //          owner nb   new  fc  fp  dfc  dfp  Flo Fhi
     // after a step: owner <- nb, nb <- new; fc <- fp; dfc <- dfp; Flo <- Fhi; (D0, D1) <- (D1, D2); (a0, a1) <- (a1, a0')
     if (CS == 4) {
-      face(f0 + 1, U, un, up, uo, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Dn, Dp, Do, an, ao);
-      face(f0 + 2, U, up, uo, un, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dp, Do, Dn, ao, an);
-      face(f0 + 3, U, uo, un, up, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Do, Dn, Dp, an, ao);
-      face(f0 + 4, U, un, up, uo, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dn, Dp, Do, ao, an);
+      face(f0 + 1, U, SHARE ? 2 : 0, un, up, uo, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Dn, Dp, Do, an, ao);
+      face(f0 + 2, U, 0, up, uo, un, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dp, Do, Dn, ao, an);
+      face(f0 + 3, U, 0, uo, un, up, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Do, Dn, Dp, an, ao);
+      face(f0 + 4, U, 0, un, up, uo, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dn, Dp, Do, ao, an);
+      if (SHARE && seg == 0) {
+        // the cell between the two threads: its low face is this thread's last (Fa, ca), its high face the upper thread's
+        asm volatile("bar.sync 1, %0;" ::"n"(NT));
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (FLUX == 0) {
+            const unsigned long long b = ((unsigned long long)__float_as_uint(sP[v * FS + hP + FACE]) << 32) | __float_as_uint(sP[v * FS + hP]);
+            Fb[v] = (FT)__longlong_as_double((long long)b);
+          } else {
+            Fb[v] = (FT)sP[v * FS + hP];
+          }
+        }
+        cell_update(Fa, Fb, ca, sD[hD]);
+      }
     } else {
 #pragma unroll 1
       for (int f = f0 + 1; f <= f0 + CS; f += 6) {
-        face(f, U, un, up, uo, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Dn, Dp, Do, an, ao);
-        face(f + 1, U, up, uo, un, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dp, Do, Dn, ao, an);
+        face(f, U, 0, un, up, uo, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Dn, Dp, Do, an, ao);
+        face(f + 1, U, 0, up, uo, un, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dp, Do, Dn, ao, an);
         if (f + 2 > f0 + CS) break;
-        face(f + 2, U, uo, un, up, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Do, Dn, Dp, an, ao);
-        face(f + 3, U, un, up, uo, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dn, Dp, Do, ao, an);
-        face(f + 4, U, up, uo, un, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Dp, Do, Dn, an, ao);
-        face(f + 5, U, uo, un, up, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Do, Dn, Dp, ao, an);
+        face(f + 2, U, 0, uo, un, up, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Do, Dn, Dp, an, ao);
+        face(f + 3, U, 0, un, up, uo, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Dn, Dp, Do, ao, an);
+        face(f + 4, U, 0, up, uo, un, fp, fc, dfn, dfo, Fa, Fb, ca, cb, Dp, Do, Dn, an, ao);
+        face(f + 5, U, 0, uo, un, up, fc, fp, dfo, dfn, Fb, Fa, cb, ca, Do, Dn, Dp, ao, an);
       }
     }
     __syncthreads();
   }
 }
 
-template <int FLUX, int SEG, int HYB, bool X2>
+template <int FLUX, int SEG, int HYB, bool X2, bool SHARE>
 int launch_march(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
                  float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
   using C = MarchCfg<SEG>;
   static bool attr = false;
   if (!attr) {
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  k_march_flux<FLUX, SEG, HYB, X2><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  k_march_flux<FLUX, SEG, HYB, X2, SHARE><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
 }
 
-template <int FLUX, int SEG>
-int launch_march_h(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, bool x2, ibx_fluid f, const float* P,
+template <int FLUX, int SEG, bool X2, bool SHARE>
+int launch_march_h(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, const float* P,
                    const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
-  if (x2) {
-    if (hyb == 0) return launch_march<FLUX, SEG, 0, true>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-    if (hyb == 1) return launch_march<FLUX, SEG, 1, true>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-    return launch_march<FLUX, SEG, 2, true>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  }
-  if (hyb == 0) return launch_march<FLUX, SEG, 0, false>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  if (hyb == 1) return launch_march<FLUX, SEG, 1, false>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  return launch_march<FLUX, SEG, 2, false>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (hyb == 0) return launch_march<FLUX, SEG, 0, X2, SHARE>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (hyb == 1) return launch_march<FLUX, SEG, 1, X2, SHARE>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  return launch_march<FLUX, SEG, 2, X2, SHARE>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+}
+
+template <int FLUX>
+int launch_march_v(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, int seg, bool x2, bool share, ibx_fluid f,
+                   const float* P, const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
+#define GO(SEG, X2, SH) return launch_march_h<FLUX, SEG, X2, SH>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st)
+  if (seg == 1) { if (x2) GO(1, true, false); GO(1, false, false); }
+  if (x2) { if (share) GO(2, true, true); GO(2, true, false); }
+  if (share) GO(2, false, true);
+  GO(2, false, false);
+#undef GO
 }
 
 }  // namespace
@@ -323,12 +372,9 @@ int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, in
   const char* e = getenv("IBX_MARCH_SEG");   // threads per pencil (1 or 2); 2 measured faster on C4
   const int seg = e && atoi(e) == 1 ? 1 : 2;
   const bool x2 = getenv("IBX_MARCH_SCALAR") == nullptr;   // IBX_MARCH_SCALAR=1: scalar FADD / FMUL instead of the packed pairs
-  if (flux_kind == 0) {
-    if (seg == 1) return launch_march_h<0, 1>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
-    return launch_march_h<0, 2>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
-  }
-  if (seg == 1) return launch_march_h<1, 1>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
-  return launch_march_h<1, 2>(c, D, blocks, n, hyb, x2, f, P, S, R, cfl, GF, GC, st);
+  const bool share = getenv("IBX_MARCH_NOSHARE") == nullptr; // IBX_MARCH_NOSHARE=1: both threads of a pencil evaluate its middle face
+  if (flux_kind == 0) return launch_march_v<0>(c, D, blocks, n, hyb, seg, x2, share, f, P, S, R, cfl, GF, GC, st);
+  return launch_march_v<1>(c, D, blocks, n, hyb, seg, x2, share, f, P, S, R, cfl, GF, GC, st);
 }
 
 }  // namespace ibx

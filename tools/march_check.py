@@ -31,8 +31,8 @@ ms = C.c_float()
 ref = None
 for label, env in (("tile kernels", {"IBX_NO_MARCH": "1"}), ("march, generic general faces", {"IBX_GEN_OLD": "1"}),
                    ("march SEG=1", {"IBX_MARCH_SEG": "1"}), ("march scalar FADD/FMUL", {"IBX_MARCH_SCALAR": "1"}),
-                   ("march (default: packed f32x2)", {})):
-    for k in ("IBX_NO_MARCH", "IBX_MARCH_SEG", "IBX_GEN_OLD", "IBX_MARCH_SCALAR"):
+                   ("march, middle face twice", {"IBX_MARCH_NOSHARE": "1"}), ("march (default)", {})):
+    for k in ("IBX_NO_MARCH", "IBX_MARCH_SEG", "IBX_GEN_OLD", "IBX_MARCH_SCALAR", "IBX_MARCH_NOSHARE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     R.fill(0.0); cfl.fill(0.0)
