@@ -18,4 +18,5 @@ from .cfd import (Fluid, FlowBC, state2primitive, primitive2state, speed_of_soun
                   residual_euler, ghost_update_euler, residual_advection, euler_step_host, euler_step_host_begin,
                   euler_step_host_end, pinned_empty)
 from .solver import FAS, Multigrid, PIPreconditioner, hutchinson_trick, Linearization, linearize, proj_along, solve  # noqa: F401
+from .vtk import export_vtk, vtk_grid_mesh, vtk_grid_stl  # noqa: F401
 from . import synthetic, turbulence  # noqa: F401

@@ -109,3 +109,26 @@ def test_rae2822_fas_multigrid_cycle(get_case, ib, oracle):
     # relative change of its input by ~1e2, and the cycle chains ~12 evaluations over three levels
     assert (np.abs(Qh - Qo) / qs).max() < 5e-4, (np.abs(Qh - Qo) / qs).max()
     assert abs(float(ratio) - float(oratio)) < 1e-3 * max(float(oratio), 1e-6), (ratio, oratio)
+
+
+def test_rae2822_export_vtk_like_the_reference_script(get_case, ib, tmp_path):
+    """The closing lines of test/rae2822.jl: `export_vtk("rae2822", dom; ny = ny)` with ny from impose_bc!, volume and
+    surface files, and the coarsest multigrid domain."""
+    import os
+    import xml.etree.ElementTree as ET
+    c = get_case("rae2822", 10_000, upload=True)
+    N = len(c.dom)
+    ny = np.zeros(N, F32)
+    ib.impose_bc(lambda b, x: b.normals.col(1), c.dom, "wall", ny)          # test/rae2822.jl:31-34
+    out = ib.export_vtk(str(tmp_path / "rae2822"), c.dom, ny=ny, surface_data={"wall": {"area": c.dom.surfaces["wall"].areas}})
+    assert len(ET.parse(out["volume"]).getroot().findall(".//DataSet")) == c.msh.nblocks == 580
+    surf = ET.parse(out["surface"]).getroot().findall(".//DataSet")
+    assert [s.get("name") for s in surf] == ["wall"]
+    piece = ET.parse(os.path.join(str(tmp_path / "rae2822"), surf[0].get("file"))).getroot().find(".//Piece")
+    named = {a.get("Name"): np.array(a.text.split(), dtype=np.float64) for tag in ("PointData", "CellData") for a in piece.find(tag)}
+    s = c.dom.surfaces["wall"]
+    assert np.allclose(named["ny"], s(ny), atol=1e-7) and np.allclose(named["area"], s.areas)
+    assert np.abs(named["ny"]).max() > 0.5                                  # the wall normals reach the surface values
+    cd, _, _ = ib.multigrid(c.dom)
+    out = ib.export_vtk(str(tmp_path / "rae2822_coarse"), cd[-1], export_surface=False)
+    assert len(ET.parse(out["volume"]).getroot().findall(".//DataSet")) == 580
