@@ -23,7 +23,8 @@ export Stereolitography, merge_points, feature_regions, DistanceField, Ball, Box
        owner_distance, neighbor_distance, face_gradient, JST_sensor, MUSCL, impose_bc!, multigrid, volume_integral,
        Fluid, FlowBC, state2primitive, primitive2state, speed_of_sound, inviscid_fluxes,
        residual_euler!, ghost_update_euler!, Transport, dynamic_viscosity, heat_conductivity, viscous_fluxes,
-       shock_sensor, shear_rate, Ducros_sensor, pressure_coefficient
+       shock_sensor, shear_rate, Ducros_sensor, pressure_coefficient, Accumulator, Interpolator, multigrid, FAS!,
+       euler_step_host!, euler_step_host_end, halo_begin!, halo_end!
 
 const libibx = get(ENV, "LIBIBX", joinpath(@__DIR__, "..", "libibx.so"))
 
@@ -422,8 +423,101 @@ end
 # ibx_smagorinsky, ibx_standard_keps, ibx_wray_agarwal, ibx_wale the same way (argument lists in include/ibx.h; the Python
 # mirror immersedboundary.jl_b200/turbulence.py is the executable statement of those bindings).
 
-"`multigrid(dom)` (src/ImmersedBoundary.jl:1355-1407): coarse Domains by `ibx_mesh_from_blocks` + IDW transfer accumulators
-by `ibx_interpolator_build`; returns `(coarse_doms, prolongators, coarseners)` like the reference code (:1406)."
-function multigrid end  # composed exactly like immersedboundary.jl_b200/domain.py:multigrid (same three ABI calls)
+# ------------------------------------------------------------------ accumulators, multigrid, FAS!, host-buffer evaluation, halo exchange
+"Device-resident `Accumulator` (src/accumulator.jl:12-130): CSR tables owned by the library; `acc(v)` is one kernel."
+mutable struct Accumulator
+    h::Ptr{Cvoid}
+    n_output::Int
+    uploaded::Bool
+end
+function Accumulator(h::Ptr{Cvoid})
+    n = Ref{Int64}(0); nnz = Ref{Int64}(0); w = Ref{Cint}(0)
+    check(ccall((:ibx_accum_info, libibx), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Cint}), h, n, nnz, w))
+    acc = Accumulator(h, n[], false)
+    finalizer(a -> ccall((:ibx_accum_free, libibx), Cint, (Ptr{Cvoid},), a.h), acc)
+end
+function (acc::Accumulator)(v::IBXArray; Δ::Bool = false)
+    acc.uploaded || (check(ccall((:ibx_accum_upload, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), context(), acc.h)); acc.uploaded = true)
+    out = length(v.dims) == 1 ? IBXArray{1}((acc.n_output,)) : IBXArray{2}((acc.n_output, ncols(v)))
+    check(ccall((:ibx_accumulate, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Int64), context(), acc.h, v.h, Δ, out.h)); out
+end
+"`Interpolator(X, Xc; linear, k)` (src/nninterp.jl:85-138); X, Xc are (nd, npoints) like the reference and are passed row-major."
+function Interpolator(X::AbstractMatrix, Xc::AbstractMatrix; linear::Bool = true, k::Int = 0)
+    Xr = Matrix{Float32}(X); Xcr = Matrix{Float32}(Xc)          # column-major (nd, n) == row-major (n, nd)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ibx_interpolator_build, libibx), Cint, (Cint, Int64, Ptr{Float32}, Int64, Ptr{Float32}, Ptr{Float32}, Cint, Cint, Ref{Ptr{Cvoid}}),
+                size(Xr, 1), size(Xr, 2), Xr, size(Xcr, 2), Xcr, C_NULL, linear, k, out))
+    Accumulator(out[])
+end
+function cell_centers(dom::Domain)
+    X = Matrix{Float32}(undef, dom.nd, dom.ncells)              # (nd, ncells) column-major == the ABI's ncells x nd row-major
+    check(ccall((:ibx_domain_cells, libibx), Cint, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}), dom.h, X, C_NULL)); X
+end
+"`multigrid(dom)` (src/ImmersedBoundary.jl:1355-1407): coarse Domains from `ibx_mesh_from_blocks`, IDW transfer accumulators from
+`ibx_interpolator_build`; returns `(coarse_doms, prolongators, coarseners)` like the reference code (:1406)."
+function multigrid(dom::Domain; max_levels::Int = 0, factor::Int = 2, domain_kwargs...)
+    msh = dom.mesh
+    max_levels = max_levels == 0 ? floor(Int, log2(msh.block_size)) : max_levels
+    coarse_doms = Domain[]; coarseners = Accumulator[]; prolongators = Accumulator[]
+    Xold = cell_centers(dom); bsize = Int(msh.block_size)
+    for _ = 1:max_levels
+        bsize ÷= factor
+        mh = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ibx_mesh_from_blocks, libibx), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), msh.h, bsize, mh))
+        cmsh = Mesh(mh[], Int32(bsize), msh.nd, length(dom) ÷ (Int(msh.block_size) ÷ bsize)^msh.nd)
+        cdom = Domain(cmsh; domain_kwargs...)
+        X = cell_centers(cdom)
+        push!(coarseners, Interpolator(Xold, X; linear = false)); push!(prolongators, Interpolator(X, Xold; linear = false))
+        push!(coarse_doms, cdom); Xold = X
+    end
+    (coarse_doms, prolongators, coarseners)
+end
+
+"`FAS!(f, Q, coarseners, prolongators; ...)` (src/solver.jl:39-91) on device arrays; keeps the `length(coarseners) > 1` condition (:60)."
+function FAS!(f, Q::IBXArray, coarseners = (), prolongators = (); prescribed_f = nothing, multigrid_level::Int = 0,
+              n_iter::Int = 50, rtol::Real = 1f-1, atol::Real = 1f-7)
+    fQ, ω = f(multigrid_level, Q)
+    source = isnothing(prescribed_f) ? nothing : prescribed_f .- fQ
+    r = isnothing(source) ? fQ : fQ .+ source
+    nr0 = norm(r); nr = nr0
+    if length(coarseners) > 1
+        Qc = coarseners[1](Q); Qcold = copy(Qc)
+        FAS!(f, Qc, coarseners[2:end], prolongators[2:end]; prescribed_f = coarseners[1](r), multigrid_level = multigrid_level + 1,
+             n_iter = n_iter, rtol = rtol, atol = atol)
+        Q .+= prolongators[1](Qc .- Qcold)
+    end
+    for _ = 1:n_iter
+        r, ω = f(multigrid_level, Q)
+        isnothing(source) || (r .+= source)
+        om = ω isa IBXArray ? ω : (o = IBXArray{1}((size(Q, 1),)); check(ccall((:ibx_array_fill, libibx), Cint, (Ptr{Cvoid}, Int64, Cfloat), context(), o.h, ω)); o)
+        check(ccall((:ibx_clamped_update, libibx), Cint, (Ptr{Cvoid}, Int64, Int64, Int64), context(), Q.h, om.h, r.h))
+        nr = norm(r)
+        nr < nr0 * rtol + atol && break
+    end
+    nr / (nr0 + eps(Float32))
+end
+
+"One evaluation with HOST arrays (pinned for asynchronous copies): H2D(Q) -> ghost updates in `bcs` order -> residual -> D2H(R, cfl)."
+struct BCSpec; boundary::Cint; normal_flow::Cint; n_pinf::Cint; Pinf::NTuple{5, Float32}; end
+BCSpec(dom::Domain, name::String, bc::FlowBC) = BCSpec(dom.boundary_index[name], bc.normal_flow, length(bc.P),
+                                                       ntuple(i -> i <= length(bc.P) ? bc.P[i] : 0.0f0, 5))
+function euler_step_host!(dom::Domain, fluid::Fluid, bcs::Vector{Pair{String, FlowBC}}, Q::Matrix{Float32}, R::Matrix{Float32},
+                          cfl::Vector{Float32}; flux_kind::Int = 0, slot::Union{Nothing, Int} = nothing)
+    specs = [BCSpec(dom, n, bc) for (n, bc) in bcs]
+    GC.@preserve specs Q R cfl begin
+        if isnothing(slot)
+            check(ccall((:ibx_euler_step_host, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Fluid, Cint, Cint, Ptr{BCSpec}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                        context(), dom.h, fluid, flux_kind, length(specs), specs, Q, R, cfl))
+        else    # two evaluations in flight: the caller keeps Q, R, cfl alive until euler_step_host_end(slot)
+            check(ccall((:ibx_euler_step_host_begin, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Fluid, Cint, Cint, Ptr{BCSpec}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cint),
+                        context(), dom.h, fluid, flux_kind, length(specs), specs, Q, R, cfl, slot))
+        end
+    end
+end
+euler_step_host_end(slot::Int) = check(ccall((:ibx_euler_step_host_end, libibx), Cint, (Ptr{Cvoid}, Cint), context(), slot))
+
+"Halo exchange of a rank-local (sharded) domain; `halo_begin!` alone may precede `residual_euler!` on the same array (it completes it)."
+halo_begin!(dom::Domain, a::IBXArray) = check(ccall((:ibx_halo_begin, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), context(), dom.h, a.h))
+halo_end!(dom::Domain, a::IBXArray) = check(ccall((:ibx_halo_end, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), context(), dom.h, a.h))
 
 end # module
