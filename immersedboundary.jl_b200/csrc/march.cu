@@ -46,7 +46,8 @@ struct MarchCfg {
 // SHARE (two threads per pencil): the middle face of a pencil is evaluated once -- the upper thread skips the flux of its
 // first face, hands the flux of its second face to the lower thread through the pencil's (by then dead) low-halo slots,
 // and the lower thread updates the cell between them; producer / consumer named barriers, no CTA-wide wait.
-template <int FLUX, int SEG, int HYB, bool X2, bool SHARE>
+// HLR: the HLL evaluation on (left, right) packed pairs (hll_flux_lr, physics.cuh)
+template <int FLUX, int SEG, int HYB, bool X2, bool SHARE, bool HLR>
 __global__ void __launch_bounds__(MarchCfg<SEG>::NT, 5)
 k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
              ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, float* __restrict__ R,
@@ -217,7 +218,8 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
         muscl_face_p2v<S, NV, NR>(qo, qn, fcc, dfc, dfp, D0, D1, pl, pr);
         if (FLUX == 0) {
           double Fd[NV];
-          hll_flux<ND, true>(fl, pl, pr, d, Fd);
+          if (HLR) hll_flux_lr<ND>(fl, pl, pr, d, Fd);
+          else hll_flux<ND, true>(fl, pl, pr, d, Fd);
 #pragma unroll
           for (int v = 0; v < NV; ++v) Fh[v] = (FT)Fd[v];
         } else {
@@ -324,37 +326,40 @@ k_march_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
   }
 }
 
-template <int FLUX, int SEG, int HYB, bool X2, bool SHARE>
+template <int FLUX, int SEG, int HYB, bool X2, bool SHARE, bool HLR>
 int launch_march(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
                  float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
   using C = MarchCfg<SEG>;
   static bool attr = false;
   if (!attr) {
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr = true;
   }
-  k_march_flux<FLUX, SEG, HYB, X2, SHARE><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
+  k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
 }
 
-template <int FLUX, int SEG, bool X2, bool SHARE>
+template <int FLUX, int SEG, bool X2, bool SHARE, bool HLR>
 int launch_march_h(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, const float* P,
                    const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
-  if (hyb == 0) return launch_march<FLUX, SEG, 0, X2, SHARE>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  if (hyb == 1) return launch_march<FLUX, SEG, 1, X2, SHARE>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
-  return launch_march<FLUX, SEG, 2, X2, SHARE>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (hyb == 0) return launch_march<FLUX, SEG, 0, X2, SHARE, HLR>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  if (hyb == 1) return launch_march<FLUX, SEG, 1, X2, SHARE, HLR>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
+  return launch_march<FLUX, SEG, 2, X2, SHARE, HLR>(c, D, blocks, n, f, P, S, R, cfl, GF, GC, st);
 }
 
 template <int FLUX>
-int launch_march_v(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, int seg, bool x2, bool share, ibx_fluid f,
-                   const float* P, const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
-#define GO(SEG, X2, SH) return launch_march_h<FLUX, SEG, X2, SH>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st)
-  if (seg == 1) { if (x2) GO(1, true, false); GO(1, false, false); }
-  if (x2) { if (share) GO(2, true, true); GO(2, true, false); }
-  if (share) GO(2, false, true);
-  GO(2, false, false);
+int launch_march_v(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, int seg, bool x2, bool share, bool hlr,
+                   ibx_fluid f, const float* P, const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
+#define GO(SEG, X2, SH, HL) return launch_march_h<FLUX, SEG, X2, SH, HL>(c, D, blocks, n, hyb, f, P, S, R, cfl, GF, GC, st)
+  if (seg == 1) { if (x2) GO(1, true, false, false); GO(1, false, false, false); }
+  if (x2) {
+    if (share) { if (hlr && FLUX == 0) GO(2, true, true, true); GO(2, true, true, false); }
+    GO(2, true, false, false);
+  }
+  if (share) GO(2, false, true, false);
+  GO(2, false, false, false);
 #undef GO
 }
 
@@ -373,8 +378,9 @@ int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, in
   const int seg = e && atoi(e) == 1 ? 1 : 2;
   const bool x2 = getenv("IBX_MARCH_SCALAR") == nullptr;   // IBX_MARCH_SCALAR=1: scalar FADD / FMUL instead of the packed pairs
   const bool share = getenv("IBX_MARCH_NOSHARE") == nullptr; // IBX_MARCH_NOSHARE=1: both threads of a pencil evaluate its middle face
-  if (flux_kind == 0) return launch_march_v<0>(c, D, blocks, n, hyb, seg, x2, share, f, P, S, R, cfl, GF, GC, st);
-  return launch_march_v<1>(c, D, blocks, n, hyb, seg, x2, share, f, P, S, R, cfl, GF, GC, st);
+  const bool hlr = getenv("IBX_MARCH_HLR") != nullptr;       // IBX_MARCH_HLR=1: HLL on (left, right) packed pairs (opt-in)
+  if (flux_kind == 0) return launch_march_v<0>(c, D, blocks, n, hyb, seg, x2, share, hlr, f, P, S, R, cfl, GF, GC, st);
+  return launch_march_v<1>(c, D, blocks, n, hyb, seg, x2, share, false, f, P, S, R, cfl, GF, GC, st);
 }
 
 }  // namespace ibx

@@ -181,6 +181,7 @@ def test_marching_kernels_bit_identical_to_tile_kernels_and_oracle(get_case, ib,
     for label, env in (("default", {}), ("tile", {"IBX_NO_MARCH": "1"}), ("generic_faces", {"IBX_GEN_OLD": "1"}),
                        ("tile_sensors", {"IBX_SENSOR_TILES": "1"}), ("one_thread_per_pencil", {"IBX_MARCH_SEG": "1"}),
                        ("scalar_fp32", {"IBX_MARCH_SCALAR": "1"}), ("middle_face_twice", {"IBX_MARCH_NOSHARE": "1"}),
+                       ("hll_on_lr_pairs", {"IBX_MARCH_HLR": "1"}),
                        ("one_stream", {"IBX_ONE_STREAM": "1"})):
         os.environ.update(env)
         try:

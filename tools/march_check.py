@@ -31,8 +31,9 @@ ms = C.c_float()
 ref = None
 for label, env in (("tile kernels", {"IBX_NO_MARCH": "1"}), ("march, generic general faces", {"IBX_GEN_OLD": "1"}),
                    ("march SEG=1", {"IBX_MARCH_SEG": "1"}), ("march scalar FADD/FMUL", {"IBX_MARCH_SCALAR": "1"}),
-                   ("march, middle face twice", {"IBX_MARCH_NOSHARE": "1"}), ("march (default)", {})):
-    for k in ("IBX_NO_MARCH", "IBX_MARCH_SEG", "IBX_GEN_OLD", "IBX_MARCH_SCALAR", "IBX_MARCH_NOSHARE"):
+                   ("march, middle face twice", {"IBX_MARCH_NOSHARE": "1"}), ("march (default)", {}),
+                   ("march, HLL on (L, R) pairs", {"IBX_MARCH_HLR": "1"}), ("march (default) again", {})):
+    for k in ("IBX_NO_MARCH", "IBX_MARCH_SEG", "IBX_GEN_OLD", "IBX_MARCH_SCALAR", "IBX_MARCH_NOSHARE", "IBX_MARCH_HLR"):
         os.environ.pop(k, None)
     os.environ.update(env)
     R.fill(0.0); cfl.fill(0.0)
