@@ -41,3 +41,29 @@ def test_compiled_cpu_baseline_equals_numpy_oracle(get_case, ib, oracle, name, m
         assert np.array_equal(Rc, Ro), (nt, int((Rc != Ro).sum()))
         assert np.array_equal(cc, co)
     assert np.array_equal(out[0][0], out[1][0])
+
+
+def test_cpu_baseline_on_builder_tables_equals_oracle_tables(get_case, ib, oracle):
+    """bench.py feeds the compiled CPU baseline with the partition / boundary tables of the host-side C++ builder (the
+    NumPy builder is too slow at bench size).  Same tables -> same bits as with the oracle's own tables; the donor
+    weights are the one place the two builders differ (float32 SVD vs double Jacobi, <= 2e-6), visible only in the
+    ghost update."""
+    from oracle import cpu_ref
+    c = get_case("rae2822", 10_000)
+    cfd = oracle.cfd
+    fl = cfd.Fluid()
+    N, nd = c.odom.centers.shape
+    Q0 = np.asfortranarray(ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers)))
+    a, b = cpu_ref.CpuRef.from_oracle(c.odom), cpu_ref.CpuRef.from_builder(c.dom)
+    out = []
+    for ref in (a, b):
+        R, cf = np.zeros((N, nd + 2), F32, order="F"), np.zeros(N, F32)
+        ref.residual(fl, Q0, R, cf, n_threads=2)
+        out.append((R, cf))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    Qa, Qb = Q0.copy(order="F"), Q0.copy(order="F")
+    a.ghost_update(fl, Qa, _bcs(cfd, fl, nd))
+    b.ghost_update(fl, Qb, _bcs(cfd, fl, nd))
+    touched = (Qa != Q0).any(axis=1)
+    assert touched.sum() > 0 and np.array_equal(touched, (Qb != Q0).any(axis=1))
+    assert (np.abs(Qa - Qb) / np.abs(Qa).max(axis=0)).max() < 2e-6
