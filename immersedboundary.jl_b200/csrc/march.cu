@@ -11,7 +11,11 @@
 //     cell changes with the marching direction) and is rounded once per dimension exactly like `R .-= green_gauss(..)`.
 // Irregular blocks (box / coarser / finer contacts) run the same loop; the faces whose 4-cell stencil touches an
 // irregular block face (the block face and the first internal face behind it) take their flux from the scratch written
-// by the general-face pass (k_hyb_flux MODE 1, tile.cu) instead of computing it.
+// by the general-face pass (k_gen_faces, gen.cu) instead of computing it.
+// Two threads share a pencil (5 + 4 faces; the middle face is evaluated once and handed over through shared memory behind
+// producer / consumer named barriers), the stencil advance and MUSCL run on packed FP32 pairs (FADD2 / FMUL2), division
+// and square root are the in-range correction sequences without their range-check branches (physics.cuh).  Every
+// variant selectable at run time (IBX_MARCH_SEG / _SCALAR / _NOSHARE / _HLR, IBX_NO_MARCH) produces the same bits.
 #include "device.cuh"
 #include "physics.cuh"
 #include "tile_common.cuh"
