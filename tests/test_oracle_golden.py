@@ -177,3 +177,35 @@ def test_geometric_multigrid_mgrid(oracle):
     one = np.ones(256, F32)
     assert np.allclose(mg.coarseners[0](one), 1.0, atol=1e-6)
     assert np.allclose(mg.prolongators[0](mg.coarseners[0](one)), 1.0, atol=1e-6)
+
+
+def test_float64_flux_promotion_is_what_the_tolerance_rests_on(get_case, ib, oracle):
+    """DESIGN.md 4.1, on the CPU: the reference's HLL line promotes the flux (and the Green-Gauss sums taken of it) to
+    Float64 (src/cfd.jl:504-507).  Rounding that flux to Float32 before the divergence -- the 'obvious' fast kernel --
+    moves the residual by more than the north-star tolerance (1e-5 relative per cell) in practically EVERY cell, because
+    a residual is a difference of fluxes ~1e3 times larger than itself.  Hence the kernels keep the promotion."""
+    from oracle import cfd
+    from oracle.domain import JST_sensor, MUSCL, cell_gradient, green_gauss
+    c = get_case("sphere3d_stl", 20_000)
+    fl = cfd.Fluid()
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
+
+    def residual(round_flux):
+        def f(part, Q, R):
+            P = cfd.state2primitive(fl, Q)
+            D = JST_sensor(part, P[:, 0])
+            R[...] = 0
+            for dim in range(part.ndims):
+                PL, PR = MUSCL(part, P, cell_gradient(part, P, dim), dim, D=D, high_order=False)
+                Fx = cfd.inviscid_fluxes_hll(fl, PL, PR, dim)
+                assert Fx.dtype == np.float64
+                R[...] = R - green_gauss(part, Fx.astype(F32) if round_flux else Fx, dim)
+        R = np.zeros_like(Q0)
+        c.odom(f, Q0.copy(), R)
+        return R
+
+    Ro, R32 = residual(False), residual(True)
+    scale = np.abs(Ro).max(axis=0)
+    rel = (np.abs(R32 - Ro) / np.maximum(np.abs(Ro), 1e-3 * scale)).max(axis=1)
+    assert (rel > 1e-5).mean() > 0.9, (rel > 1e-5).mean()
+    assert (np.abs(R32 - Ro) / scale).max() < 1e-3          # ... while looking perfectly fine at the scale of the field
