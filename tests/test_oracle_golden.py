@@ -209,3 +209,46 @@ def test_float64_flux_promotion_is_what_the_tolerance_rests_on(get_case, ib, ora
     rel = (np.abs(R32 - Ro) / np.maximum(np.abs(Ro), 1e-3 * scale)).max(axis=1)
     assert (rel > 1e-5).mean() > 0.9, (rel > 1e-5).mean()
     assert (np.abs(R32 - Ro) / scale).max() < 1e-3          # ... while looking perfectly fine at the scale of the field
+
+
+def test_one_fma_contraction_already_breaks_the_tolerance(get_case, ib, oracle):
+    """The other half of DESIGN.md 4.1: Julia does not contract `a * b + c`; a GPU compiler does by default.  Fusing a
+    SINGLE multiply-add of the reference -- the sensor blend of MUSCL, `uL * Df + (1 - Df) * uf`
+    (src/ImmersedBoundary.jl:1150-1153), evaluated here with one rounding instead of two -- already moves the residual
+    of a large share of the cells by more than 1e-5 relative.  Hence `-fmad=false` and the scalar adds behind the
+    packed products."""
+    from oracle import cfd
+    import oracle.domain as od
+    c = get_case("sphere3d_stl", 20_000)
+    fl = cfd.Fluid()
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
+
+    def muscl_fused_blend(part, u, du, dim, D):
+        down, dnei = od.owner_distance(part, dim), od.neighbor_distance(part, dim)
+        uo, un = od.at_owners(part, u, dim), od.at_neighbors(part, u, dim)
+        col = lambda a: od._col(a, uo)
+        gf = (un - uo) / col(down + dnei)
+        duo, dun = od.at_owners(part, du, dim), od.at_neighbors(part, du, dim)
+        s = od.minmod((2 * dun - gf) * col(dnei), (2 * duo - gf) * col(down))
+        Df = col(np.maximum(np.maximum(od.at_owners(part, D, dim), od.at_neighbors(part, D, dim)), F32(1e-7)))
+        t = (F32(1.0) - Df) * ((uo * col(dnei) + un * col(down)) / col(down + dnei))
+        fma = lambda a, b, c_: (a.astype(np.float64) * b.astype(np.float64) + c_.astype(np.float64)).astype(F32)   # one rounding
+        return fma(uo + s, Df + 0 * uo, t), fma(un - s, Df + 0 * uo, t)
+
+    def residual(fused):
+        def f(part, Q, R):
+            P = cfd.state2primitive(fl, Q)
+            D = od.JST_sensor(part, P[:, 0])
+            R[...] = 0
+            for dim in range(part.ndims):
+                g = od.cell_gradient(part, P, dim)
+                PL, PR = muscl_fused_blend(part, P, g, dim, D) if fused else od.MUSCL(part, P, g, dim, D=D, high_order=False)
+                R[...] = R - od.green_gauss(part, cfd.inviscid_fluxes_hll(fl, PL, PR, dim), dim)
+        R = np.zeros_like(Q0)
+        c.odom(f, Q0.copy(), R)
+        return R
+
+    Ro, Rf = residual(False), residual(True)
+    scale = np.abs(Ro).max(axis=0)
+    rel = (np.abs(Rf - Ro) / np.maximum(np.abs(Ro), 1e-3 * scale)).max(axis=1)
+    assert (rel > 1e-5).mean() > 0.2, (rel > 1e-5).mean()
