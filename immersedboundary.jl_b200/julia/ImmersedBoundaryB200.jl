@@ -24,7 +24,8 @@ export Stereolitography, merge_points, feature_regions, DistanceField, Ball, Box
        Fluid, FlowBC, state2primitive, primitive2state, speed_of_sound, inviscid_fluxes,
        residual_euler!, ghost_update_euler!, Transport, dynamic_viscosity, heat_conductivity, viscous_fluxes,
        shock_sensor, shear_rate, Ducros_sensor, pressure_coefficient, Accumulator, Interpolator, multigrid, FAS!,
-       euler_step_host!, euler_step_host_end, halo_begin!, halo_end!
+       euler_step_host!, euler_step_host_end, halo_begin!, halo_end!, wall_function, Smagorinsky_νSGS, standard_kϵ,
+       Wray_Agarwal, WALE_νSGS
 
 const libibx = get(ENV, "LIBIBX", joinpath(@__DIR__, "..", "libibx.so"))
 
@@ -419,9 +420,44 @@ function pressure_coefficient(fluid::Fluid, p::IBXArray, p∞::Real, M∞::Real)
     out = similar(p)
     check(ccall((:ibx_pressure_coefficient, libibx), Cint, (Ptr{Cvoid}, Cfloat, Int64, Cfloat, Cfloat, Int64), context(), fluid.γ, p.h, p∞, M∞, out.h)); out
 end
-# src/turbulence.jl: wall_function, Smagorinsky_νSGS, standard_kϵ, Wray_Agarwal, WALE_νSGS bind ibx_wall_function(_rey),
-# ibx_smagorinsky, ibx_standard_keps, ibx_wray_agarwal, ibx_wale the same way (argument lists in include/ibx.h; the Python
-# mirror immersedboundary.jl_b200/turbulence.py is the executable statement of those bindings).
+# ---- src/turbulence.jl
+"Mirror of `ibx_wall_params` (include/ibx.h): the keyword constants of `wall_function` (src/turbulence.jl:27-33)."
+struct WallParams; κ::Float32; C::Float32; A::Float32; β::Float32; βstar::Float32; D::Float32; A⁺::Float32; ω::Float32; n_iter::Cint; end
+WallParams(; κ = 0.41f0, C = 4.9f0, A = 19.0f0, β = 0.075f0, βstar = 0.09f0, D = 4.2f0, A⁺ = 360.0f0, ω_fixed_point = 0.5f0, n_iter = 20) =
+    WallParams(κ, C, A, β, βstar, D, A⁺, ω_fixed_point, n_iter)
+function wall_function(Rey::IBXArray; kwargs...)
+    o = ntuple(_ -> similar(Rey), 5)
+    check(ccall((:ibx_wall_function_rey, libibx), Cint, (Ptr{Cvoid}, WallParams, Int64, Int64, Int64, Int64, Int64, Int64),
+                context(), WallParams(; kwargs...), Rey.h, o[1].h, o[2].h, o[3].h, o[4].h, o[5].h))
+    (y⁺ = o[1], u⁺ = o[2], μ⁺ = o[3], k⁺ = o[4], du⁺!dy⁺ = o[5])
+end
+function wall_function(y::IBXArray, u::IBXArray, ν::IBXArray; kwargs...)
+    o = ntuple(_ -> similar(y), 6)
+    check(ccall((:ibx_wall_function, libibx), Cint, (Ptr{Cvoid}, WallParams, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64, Int64),
+                context(), WallParams(; kwargs...), y.h, u.h, ν.h, o[1].h, o[2].h, o[3].h, o[4].h, o[5].h, o[6].h))
+    (uτ = o[1], νₜ = o[2], k = o[3], ω = o[4], ϵ = o[5], du!dn = o[6])
+end
+function Smagorinsky_νSGS(Δ::IBXArray, S::IBXArray; Cₛ::Real = 0.17f0)
+    out = similar(S)
+    check(ccall((:ibx_smagorinsky, libibx), Cint, (Ptr{Cvoid}, Int64, Int64, Cfloat, Int64), context(), Δ.h, S.h, Cₛ, out.h)); out
+end
+function standard_kϵ(k::IBXArray, ϵ::IBXArray, S::IBXArray; Cμ = 0.09f0, σk = 1.0f0, σϵ = 1.3f0, C1ϵ = 1.44f0, C2ϵ = 1.92f0)
+    o = ntuple(_ -> similar(k), 5)
+    check(ccall((:ibx_standard_keps, libibx), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Int64, Int64, Int64, Int64, Int64),
+                context(), k.h, ϵ.h, S.h, Cμ, σk, σϵ, C1ϵ, C2ϵ, o[1].h, o[2].h, o[3].h, o[4].h, o[5].h))
+    (νk = o[1], νϵ = o[2], Sk = o[3], Sϵ = o[4], νₜ = o[5])
+end
+function Wray_Agarwal(R::IBXArray, S::IBXArray, ∇R::IBXArray, ∇S::IBXArray; σR = 0.72f0, C₁ = 0.0829f0, κ = 0.41f0)
+    νR = similar(R); So = similar(R)
+    check(ccall((:ibx_wray_agarwal, libibx), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cfloat, Cfloat, Cfloat, Int64, Int64),
+                context(), R.h, S.h, ∇R.h, ∇S.h, σR, C₁, κ, νR.h, So.h))
+    (νₜ = R, νR = νR, S = So)
+end
+function WALE_νSGS(Δ::IBXArray, g::AbstractMatrix; Cw::Real = 0.325f0)
+    @assert size(g, 1) == 3 "WALE model only implemented for 3D"
+    out = similar(Δ); hs = _grad_table(g)
+    GC.@preserve hs check(ccall((:ibx_wale, libibx), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Cfloat, Int64), context(), Δ.h, hs, Cw, out.h)); out
+end
 
 # ------------------------------------------------------------------ accumulators, multigrid, FAS!, host-buffer evaluation, halo exchange
 "Device-resident `Accumulator` (src/accumulator.jl:12-130): CSR tables owned by the library; `acc(v)` is one kernel."
