@@ -5,7 +5,7 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the restated reference path (NumPy oracle)
 
 Workload (BASELINE.json configs[3], SURVEY.md 8d "C4"): 3-D sphere octree, box (-16)^3..16^3, block_size 8,
-growth_ratio 2, sphere radius 0.5 (analytic surface), finest cell width 32/2^10/8 inside Ball(0, r); r = 0.75
+growth_ratio 2, wall = icosphere STL (6 subdivisions, 81 920 triangles, radius 0.5), finest cell width 32/2^10/8 inside Ball(0, r); r = 0.75
 gives 50.2 M cells on one GPU and is enlarged so that the cell count grows with the number of GPUs (weak
 scaling, ~50 M cells per GPU).  Inputs: the smooth synthetic state of SURVEY.md 8(d), seed 12345.
 One step = halo exchange + ghost update (wall, farfield) + halo exchange + residual on every rank.
@@ -33,13 +33,26 @@ B_ALG = 4 * (2 * 5 + 1)                  # 44 B per cell-update: 
 B_GHOST = 4 * (5 + 5) + 8 * (4 + 4) + 4 * (3 + 1)   # 120 B per ghost
 
 
-def build_mesh(ib, radius, h=H_FINE):
-    return ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(h)),
-                   refinement_regions=[(ib.Ball([0, 0, 0], radius), F32(h))])
+STL_SUBDIV = 6                           # icosphere subdivisions of the wall STL (81 920 triangles)
+WORKLOAD = ("C4: 3-D sphere octree Euler residual (MUSCL + JST sensor + HLL) + IB ghost update (wall, farfield); wall = icosphere "
+            "STL, 81 920 triangles, radius 0.5")
+
+
+def build_mesh(ib, radius, h=H_FINE, analytic=False):
+    """C4 recipe: the wall is an icosphere STL refined by the reference's own `refine_to_length` rule inside
+    `Mesh`; `analytic=True` swaps in the exact sphere (an extension of this library, kept for quick smoke runs)."""
+    if analytic:
+        surf = ib.Sphere([0, 0, 0], 0.5)
+    else:
+        pts, tri = ib.synthetic.icosphere(STL_SUBDIV, 0.5)
+        surf = ib.Stereolitography(pts, tri)
+    return ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", surf, F32(h)), refinement_regions=[(ib.Ball([0, 0, 0], radius), F32(h))])
 
 
 def radius_for(ib, target_cells, h=H_FINE):
-    """Smallest refinement-ball radius (on a 1/64 grid) whose mesh has at least `target_cells` cells."""
+    """Smallest refinement-ball radius (on a 1/64 grid) whose mesh has at least `target_cells` cells.  The block list
+    around the ball does not depend on how the sphere surface is represented (the ball contains it), so the search
+    runs on the analytic sphere."""
     if target_cells <= 50_300_000 and h == H_FINE:
         return 0.75
     lo, hi = 0.5, 4.0
@@ -47,7 +60,7 @@ def radius_for(ib, target_cells, h=H_FINE):
         mid = round((lo + hi) / 2 * 64) / 64
         if mid in (lo, hi):
             break
-        if len(build_mesh(ib, mid, h)) >= target_cells:
+        if len(build_mesh(ib, mid, h, analytic=True)) >= target_cells:
             hi = mid
         else:
             lo = mid
@@ -55,37 +68,63 @@ def radius_for(ib, target_cells, h=H_FINE):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons polled through NVML every ~5 ms from a thread, started BEFORE the warm-up so
+    that a sub-100 ms timed region is still covered (B200_PROFILING.md's clocks line; nvidia-smi -lms cannot go that fast).
+    Only the samples between mark_begin() and mark_end() enter the median."""
 
     def __init__(self, device):
-        self.rows, self.proc, self.device = [], None, device
+        self.rows, self.device, self.stop_flag, self.thread = [], device, False, None
+        self.t0 = self.t1 = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[device])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            self.nv = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0, nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == "Active" for r in self.rows)]
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)] or self.rows
+        sm = [r[1] for r in rows]
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = [n for n, b in bits.items() if any(r[3] & b for r in rows)]
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "power_w_max": max(r[2] for r in rows) if rows else None,
+                "samples": len(sm), "samples_total": len(self.rows), "reasons": reasons, "how": "NVML polled every ~5 ms during the timed region"}
 
 
 def measured_peak_gbs():
@@ -96,85 +135,85 @@ def measured_peak_gbs():
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference(ball_radius, steps, warmup):
-    """The restated reference path on the host cores, on a BOUNDED sample: the same sphere-octree recipe at a coarser
-    size.  Compiled C + OpenMP restatement (oracle/cpu_ref.c: one task per partition like ThreadTools.tmap, gather ->
-    array-at-a-time operators with temporaries -> scatter; bit-identical to the NumPy oracle,
-    tests/test_oracle_cpu_ref.py); the NumPy oracle itself if no C compiler is available."""
-    import oracle
-    from oracle import cfd as ocfd, euler as oeuler
-    from immersedboundary_jl_b200 import synthetic
-    cores = os.cpu_count() or 1
-    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
-    fl = ocfd.Fluid()
-    a = np.sqrt(1.4 * 283.0 * 288.15)
-    Pinf = np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)
-    bcs = [("wall", ocfd.FlowBC(fl, Pinf[:3] * np.array([1, 1, 0], F32), normal_flow=True)), ("farfield", ocfd.FlowBC(fl, Pinf))]
+def _mem_available_gb():
     try:
-        from oracle import cpu_ref
-        cpu_ref.build()
-        compiled = True
-    except Exception:
-        compiled = False
-    if compiled:
-        # tables from the product's HOST-side C++ builder (no GPU involved; identical to the oracle's own tables,
-        # tests/test_builder_parity.py) -- the NumPy builder is too slow for a multi-million-cell sample
-        import immersedboundary_jl_b200 as ib
-        h = F32(0.125)
-        msh = ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", ib.Sphere([0, 0, 0], 0.5), h),
-                      refinement_regions=[(ib.Ball([0, 0, 0], 2.0 * ball_radius), h)])
-        n = len(msh)
-        dom = ib.Domain(msh, max_partition_size=max(4096, n // (4 * cores) + 1), hypercube_families=fams, build_partitions=True,
-                        build_surfaces=False, upload=False)
-        ref = cpu_ref.CpuRef.from_builder(dom)
-        Q = np.asfortranarray(synthetic.primitive2state_host(synthetic.euler_state(dom.cells()[0])))
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def cpu_reference(level, radius, steps, warmup, stl=None):
+    """The restated reference path on all host cores (oracle/cpu_ref.c: compiled C + OpenMP, one task per partition like
+    ThreadTools.tmap, gather -> array-at-a-time operators with temporaries -> scatter; bit-identical to the NumPy oracle,
+    tests/test_oracle_cpu_ref.py) on the bench's own sphere-octree recipe at octree level `level`.
+
+    The partition / boundary tables and the input state come from tools/dump_cpu_tables.py, run as a SEPARATE, untimed
+    process: this process never loads libibx.so (the reference arm must not depend on the product)."""
+    import shutil
+    import tempfile
+    from oracle import cfd as ocfd, cpu_ref
+    cores = os.cpu_count() or 1
+    cpu_ref.build()
+    tmp = tempfile.mkdtemp(prefix="ibx_cpu_tables_")
+    try:
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "dump_cpu_tables.py"), tmp, str(level), str(radius), str(400_000)]
+        if stl is not None:
+            cmd += ["stl", str(stl)]
+        subprocess.run(cmd, check=True, cwd=ROOT)
+        ref, Q, meta = cpu_ref.CpuRef.from_dump(tmp)
+        n, nparts = meta["ncells"], len(meta["parts"])
+        fl = ocfd.Fluid()
+        a = np.sqrt(1.4 * 283.0 * 288.15)
+        Pinf = np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)
+        bcs = [("wall", ocfd.FlowBC(fl, Pinf[:3] * np.array([1, 1, 0], F32), normal_flow=True)), ("farfield", ocfd.FlowBC(fl, Pinf))]
         R, cf = np.zeros((n, 5), F32, order="F"), np.zeros(n, F32)
-        nparts = len(dom.partitions)
 
         def step():
             ref.ghost_update(fl, Q, bcs, cores)
             ref.residual(fl, Q, R, cf, cores)
-        what = ("compiled C + OpenMP restatement of the reference operators (oracle/cpu_ref.c; partition tables from the "
-                "host-side C++ builder, outside the timed region)")
-    else:
-        OM = oracle.mesher
-        h = F32(0.25)
-        msh = OM.Mesh([-16, -16, -16], [32, 32, 32], ("wall", OM.AnalyticSphere([0, 0, 0], 0.5), h),
-                      refinement_regions=[(OM.Ball([0, 0, 0], ball_radius), h)])
-        dom = oracle.domain.Domain(msh, max_partition_size=max(4096, len(msh) // max(cores, 1) + 1), hypercube_families=fams)
-        Q = synthetic.primitive2state_host(synthetic.euler_state(dom.centers))
-        R, cf = np.zeros_like(Q), np.zeros(len(Q), F32)
-        res = oeuler.euler_residual(fl)
-        n, nparts = len(Q), len(dom.partitions)
 
-        def step():
-            oeuler.euler_ghost_update(dom, fl, Q, bcs)
-            dom(res, Q, R, cf, n_threads=cores)
-        what = "NumPy restatement of the reference operators"
-
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    assert "libibx.so" not in open("/proc/self/maps").read() or "immersedboundary_jl_b200" in sys.modules
     return {"value": n * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-            "sample": f"{what} (Julia cannot run here), same sphere-octree recipe at h={float(h)} -> {n} cells in "
-                      f"{nparts} partitions, {steps} evaluations (ghost update + residual), {cores} threads "
-                      f"(one task per partition, like tmap)",
-            "ms_per_step": dt / steps * 1e3, "cells": n}
+            "sample": f"compiled C + OpenMP restatement of the reference operators (oracle/cpu_ref.c; Julia cannot run here), the "
+                      f"bench's sphere-octree recipe ({meta['surface']}) at octree level {level}, refinement ball {radius} -> {n} cells "
+                      f"in {nparts} partitions, {steps} evaluations (ghost update + residual) after {warmup} warm-up, {cores} threads "
+                      f"(one task per partition, like tmap); tables built by an untimed helper process",
+            "ms_per_step": dt / steps * 1e3, "cells": n, "level": level}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference(3.5, max(1, min(args.steps, 20)), min(args.warmup, 1))
+    # the benched mesh itself (level 10, 50.2 M cells) when the host has the memory for its tables (~45 GB peak in the helper
+    # process), else one octree level coarser at a ball radius giving ~20 M cells
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    r = None
+    stl = None if args.analytic_sphere else STL_SUBDIV
+    if args.level != 10:
+        r = cpu_reference(args.level, 0.75, steps, warmup, stl)           # smoke runs / unit test of the contract line
+    elif _mem_available_gb() > 110:
+        try:
+            r = cpu_reference(10, 0.75, steps, warmup, stl)
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"[bench] full-size CPU arm failed ({e}); falling back to the level-9 sample\n")
+    if r is None:
+        r = cpu_reference(9, 1.0, steps, warmup, stl)
     line = {"impl": "reference", "metric": "cell-updates/s (Euler residual+IB)", "value": r["value"], "unit": "cell-updates/s",
-            "n_gpus": args.gpus, "steps": max(1, min(args.steps, 20)), "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "3-D sphere octree Euler (HLL + MUSCL + JST) + IB ghost update, bounded CPU sample",
-                       "cells": r["cells"]},
+            "config": {"workload": WORKLOAD + " -- CPU arm", "cells": r["cells"], "finest_level": r["level"], "block_size": 8, "nv": 5},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -198,7 +237,7 @@ def run_ours(args):
     cells_target = args.cells if args.cells else CELLS_PER_GPU * world
     h = 32.0 / 2 ** args.level / 8 * 1.01
     radius = radius_for(ib, cells_target, h) if not args.radius else args.radius
-    msh = build_mesh(ib, radius, h)
+    msh = build_mesh(ib, radius, h, analytic=args.analytic_sphere)
     fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
     gdom = ib.Domain(msh, max_partition_size=len(msh), hypercube_families=fams, build_partitions=False,
                      build_surfaces=False, upload=False, for_rank=(rank, world) if world > 1 else None)
@@ -234,6 +273,7 @@ def run_ours(args):
     Q = ib.DeviceArray(n_local, 5, False).upload(Q_host)
     R, cfl = ib.DeviceArray(n_local, 5, False), ib.DeviceArray(n_local, 1, True)
     n_ghost = sum(b.nghost for bs in dom.boundaries.values() for b in bs.values())
+    n_tied = {name: int(sum(b.n_tied for b in bs.values())) for name, bs in dom.boundaries.items()} if world == 1 else None
     setup_s = time.perf_counter() - t_setup
 
     def step():
@@ -250,18 +290,20 @@ def run_ours(args):
             dist.barrier()
         ib.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     l0 = ib.launch_count()
+    sampler.mark_begin()
     ib._lib.call("ibx_timer_start", ctx)
     for _ in range(args.steps):
         step()
     ms = C.c_float()
     ib._lib.call("ibx_timer_stop", ctx, C.byref(ms))
+    sampler.mark_end()
     barrier()
     launches = ib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
@@ -365,13 +407,15 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(3.5, 10, 1)
+        # bounded sample: the same recipe one octree level coarser (10.3 M cells), ~10-30 s of CPU work
+        r = cpu_reference(9, 0.75, 8, 1, None if args.analytic_sphere else STL_SUBDIV)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
         "metric": "cell-updates/s (Euler residual+IB)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4: 3-D sphere octree Euler residual (MUSCL + JST sensor + HLL) + IB ghost update (wall, farfield)",
+        "config": {"workload": WORKLOAD if not args.analytic_sphere else WORKLOAD.split(";")[0] + "; wall = analytic sphere (smoke option)",
+                   "ghosts_with_tied_donor_candidates": n_tied,
                    "cells": n_global, "cells_per_gpu": n_owned, "ghost_cells_rank0": n_ghost, "blocks": msh.nblocks,
                    "refinement_ball_radius": radius, "finest_level": args.level, "block_size": 8, "nv": 5, "partition": "contiguous block ranges, one per GPU",
                    "l2": "working set >> 126 MB L2, no flush needed", "setup_s": round(setup_s, 1)},
@@ -399,6 +443,7 @@ if __name__ == "__main__":
     ap.add_argument("--radius", type=float, default=0.0, help="override the refinement-ball radius (debugging)")
     ap.add_argument("--level", type=int, default=10, help="finest octree level (10 = the C4 workload; lower for smoke runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--analytic-sphere", action="store_true", help="exact sphere instead of the icosphere STL wall (quick smoke runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

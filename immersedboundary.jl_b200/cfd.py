@@ -185,9 +185,17 @@ def residual_euler(dom, fluid, Q, R, cfl, flux="hll"):
 def ghost_update_euler(dom, fluid, Q, bcs):
     """IB ghost update of the conservative state for ``bcs = [(boundary name, FlowBC), ...]`` in order."""
     dom.upload()
+    coupled = (getattr(dom, "shard_info", None) or {}).get("coupled_families")
+    done = []
     for name, bc in bcs:
+        if coupled and any((e, name) in coupled for e in done):
+            # a ghost of this family reads, on another rank, a ghost of a family applied above: refresh the halo rows
+            # so that the sequence equals the reference's successive impose_bc! calls on one array
+            dom.halo_exchange(Q)
+            done = []
         call("ibx_ghost_update_euler", context(), dom._h, dom.boundary_index[name], fluid.c, ptr(bc.P), len(bc.P),
              int(bc.normal_flow), Q.h)
+        done.append(name)
 
 
 def residual_advection(dom, u, Cvel, ud, spec):

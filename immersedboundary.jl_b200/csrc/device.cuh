@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <unordered_map>
+#include <unordered_set>
 #include <mutex>
 #include "ibx_internal.h"
 
@@ -20,6 +21,7 @@ struct ibx_ctx {
   std::unordered_map<int64_t, Arr> arrays;
   int64_t next_handle = 1;
   std::mutex mu;
+  std::unordered_set<const void*> smem_attr_done;   // kernels whose dynamic shared-memory limit is set on THIS device
   // scratch for reductions
   double* d_red = nullptr;
   double* h_red = nullptr;  // pinned
@@ -95,6 +97,20 @@ int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, in
     cudaError_t e_ = cudaGetLastError();                                         \
     if (e_ != cudaSuccess) return ibx::cuda_fail(c, e_, "kernel launch", __FILE__, __LINE__); \
   } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: remember it per context (one context
+// per device), not per process, and under the context lock (entry points may be called from several host threads).
+inline int ensure_dyn_smem(ibx_ctx* c, const void* fn, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->smem_attr_done.count(fn)) return IBX_OK;
+  }
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->smem_attr_done.insert(fn);
+  return IBX_OK;
+}
 
 inline int grid_for(int64_t n, int block, int sm_count, int per_sm = 16) {
   int64_t g = (n + block - 1) / block;

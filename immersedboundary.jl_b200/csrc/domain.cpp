@@ -4,6 +4,8 @@
 // reference's KD-tree `inrange` over all cells is replaced by block-level candidate search followed by
 // the reference's own float32 tests on the same float32 values, so the resulting sets are identical.
 #include "ibx_internal.h"
+#include <cstdio>
+#include <cstdlib>
 
 #include <numeric>
 #include <unordered_map>
@@ -526,7 +528,8 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
     std::vector<int64_t> sidx((size_t)n * k);
     std::vector<float> sw((size_t)n * k);
     std::vector<int32_t> cnt(n + 1, 0);
-#pragma omp parallel for schedule(dynamic, 256)
+    int64_t n_tied = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : n_tied)
     for (int64_t g = 0; g < n; ++g) {
       int64_t c = B.ghost[g];
       float nrm[3], acc = 0.f, img[3];
@@ -545,12 +548,17 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
       }
       B.ghost_dist[g] = gd;
       B.image_dist[g] = idist;
-      int64_t idx[16];
-      float dd[16];
+      int64_t idx[17];
+      float dd[17];
       double cw = std::max({(double)W[c * nd], (double)W[c * nd + 1], nd > 2 ? (double)W[c * nd + 2] : 0.0});
-      int found = bi.knn(img, k, 1.5 * cw, idx, dd);
+      // one candidate more than needed: a k-th / (k+1)-th distance tie is the only place where NearestNeighbors.jl's
+      // traversal order (not reproducible) could select another donor than the (distance, index) rule
+      int found = bi.knn(img, k + 1, 1.5 * cw, idx, dd);
+      if (found == k + 1 && dd[k - 1] == dd[k]) ++n_tied;
+      found = std::min(found, k);
       cnt[g + 1] = stencil_weights(C, nd, idx, found, img, true, &sidx[g * k], &sw[g * k]);
     }
+    B.n_tied = n_tied;
     for (int64_t g = 0; g < n; ++g) cnt[g + 1] += cnt[g];
     B.ptr = cnt;
     std::vector<int32_t> gidx((size_t)cnt[n]);
@@ -619,14 +627,15 @@ static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr,
   {
     std::vector<float>& lp = tproj[omp_get_thread_num()];
     std::vector<int32_t>& lg = tghost[omp_get_thread_num()];
-#pragma omp for schedule(static)
+    // the work sits in the few cells near the surface: dynamic chunks, order restored below
+#pragma omp for schedule(dynamic, 4096)
     for (int64_t i = r0; i < r1; ++i) {
       double x[3];
       for (int d = 0; d < nd; ++d) x[d] = C[i * nd + d];
       float diam = diam_of(W + i * nd, nd);
       float lim2 = diam * glr * 2.0f;
-      Num dist = df.distance(x, true);
-      if (!(dist.v <= (double)lim2)) continue;
+      Num dist;
+      if (!df.distance_within(x, true, (double)lim2, &dist)) continue;   // == !(df.distance(x) <= lim2), src/ImmersedBoundary.jl:208
       double p[3];
       df.projection(x, true, (double)lim2, p);
       float pf[3], acc = 0.f;
@@ -642,10 +651,15 @@ static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr,
       }
     }
   }
-  // static schedule => thread t holds an ascending contiguous chunk: concatenating keeps cell order
-  for (size_t t = 0; t < tghost.size(); ++t) {
-    ghosts.insert(ghosts.end(), tghost[t].begin(), tghost[t].end());
-    projs.insert(projs.end(), tproj[t].begin(), tproj[t].end());
+  // ghosts in ascending cell order (src/ImmersedBoundary.jl:229 keeps the order of the cell loop)
+  std::vector<std::pair<int32_t, std::pair<int, int64_t>>> order;   // (cell, (thread, position))
+  for (size_t t = 0; t < tghost.size(); ++t)
+    for (size_t j = 0; j < tghost[t].size(); ++j) order.push_back({tghost[t][j], {(int)t, (int64_t)j}});
+  std::sort(order.begin(), order.end());
+  for (const auto& o : order) {
+    ghosts.push_back(o.first);
+    const float* q = tproj[o.second.first].data() + o.second.second * nd;
+    projs.insert(projs.end(), q, q + nd);
   }
 }
 
@@ -707,10 +721,20 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
   D->centers.resize((size_t)D->ncells * nd);
   D->widths.resize((size_t)D->ncells * nd);
   mesh_cells(*m, D->centers.data(), D->widths.data());
+  // the reference prints its build phases when `verbose` (src/ImmersedBoundary.jl:589,705,767); here: IBX_BUILD_VERBOSE=1
+  const bool verbose = getenv("IBX_BUILD_VERBOSE") != nullptr;
+  double t_phase = omp_get_wtime();
+  auto phase = [&](const char* what) {
+    if (verbose) fprintf(stderr, "[ibx build] %-28s %8.2f s\n", what, omp_get_wtime() - t_phase);
+    t_phase = omp_get_wtime();
+  };
   BlockIndex bi;
   bi.build(*m, D->centers.data());
+  phase("cells + block index");
   build_faces(*D, bi, build_partitions_flag != 0);
+  phase("faces / block contacts");
   if (build_partitions_flag) build_partitions(*D, max_partition_size, skirt_depth);
+  phase("partitions");
   // boundaries: hypercube families first, then one per surface (src/ImmersedBoundary.jl:716-741)
   for (int f = 0; f < nfam; ++f) {
     std::vector<std::pair<int, int>> faces;
@@ -721,9 +745,11 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
     std::vector<int32_t> ghosts;
     std::vector<float> projs;
     ghosts_hcube(*D, faces, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
+    phase("hypercube ghosts");
     BoundaryFamily fam;
     fam.name = fam_names[f];
     build_boundary(*D, bi, ghosts, projs, max_partition_size, ghost_layer_ratio, fam);
+    phase("hypercube donors + weights");
     D->boundaries.push_back(std::move(fam));
   }
   for (size_t s = 0; s < m->surf_names.size(); ++s) {
@@ -731,9 +757,11 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
     std::vector<int32_t> ghosts;
     std::vector<float> projs;
     ghosts_surface(*D, df, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
+    phase("surface ghosts + projections");
     BoundaryFamily fam;
     fam.name = m->surf_names[s];
     build_boundary(*D, bi, ghosts, projs, max_partition_size, ghost_layer_ratio, fam);
+    phase("surface donors + weights");
     D->boundaries.push_back(std::move(fam));
     if (!build_surfaces || !df.stl) continue;
     // Surface (src/ImmersedBoundary.jl:743-763)
@@ -923,6 +951,16 @@ int ibx_boundary_info(const ibx_domain* d, int b, int part, int64_t* nghost, int
   *nghost = (int64_t)B.ghost.size();
   *n_image_domain = (int64_t)B.image_domain.size();
   *nnz = (int64_t)B.idx.size();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_boundary_tie_count(const ibx_domain* d, int b, int part, int64_t* n_tied) {
+  IBX_TRY
+  DOM(d);
+  IBX_REQUIRE(b >= 0 && b < (int)D.boundaries.size(), "boundary index out of range");
+  IBX_REQUIRE(part >= 0 && part < (int)D.boundaries[b].parts.size(), "boundary partition out of range");
+  *n_tied = D.boundaries[b].parts[part].n_tied;
   return IBX_OK;
   IBX_CATCH
 }

@@ -615,6 +615,9 @@ static int e2e_slot_prepare(ibx_ctx* c, ibx_ctx::E2ESlot& S, int64_t N, int nv) 
     if ((rc = ibx_array_alloc(c, N, nv, &S.Q))) return rc;
     if ((rc = ibx_array_alloc(c, N, nv, &S.R))) return rc;
     if ((rc = ibx_array_alloc(c, N, 1, &S.cfl))) return rc;
+    // ibx_array_alloc clears the new arrays on the compute stream; the upload below runs on h2d_stream and must not be
+    // overtaken by that memset (it may sit behind the other slot's residual): finish it before the slot is used.
+    CU(cudaStreamSynchronize(c->stream));
   }
   return IBX_OK;
 }

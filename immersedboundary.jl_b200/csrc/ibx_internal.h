@@ -53,15 +53,26 @@ struct KDTree {
   std::vector<double> pts;  // n x nd
   struct Node { int dim; double split; int64_t lo, hi, left, right; };
   std::vector<Node> nodes;
+  std::vector<double> bbox;  // per node: min[nd], max[nd] of its points (tight lower bounds also for far-away queries)
   std::vector<int64_t> perm;
 
   void build(int nd_, int64_t n_, const double* p, bool f32_);
   void build_f(int nd_, int64_t n_, const float* p);
   double d2(int64_t i, const double* x, bool xf32) const;
   // k nearest: idx/d2 sorted ascending by (d2, idx); returns number found (min(k, n))
-  int knn(const double* x, bool xf32, int k, int64_t* idx, double* d2out) const;
+  // max_d2: only points with d2 <= max_d2 are of interest (prunes the search of far-away queries from the start)
+  int knn(const double* x, bool xf32, int k, int64_t* idx, double* d2out, double max_d2 = 1e300) const;
   // all points with d2 <= r^2 (inclusive), ascending index
   void inrange(const double* x, bool xf32, double r, std::vector<int64_t>& out) const;
+  double box_d2(int64_t node, const double* x) const {
+    const double* b = &bbox[(size_t)node * 2 * nd];
+    double acc = 0;
+    for (int d = 0; d < nd; ++d) {
+      double t = x[d] < b[d] ? b[d] - x[d] : (x[d] > b[nd + d] ? x[d] - b[nd + d] : 0.0);
+      acc += t * t;
+    }
+    return acc;
+  }
  private:
   int64_t build_rec(int64_t lo, int64_t hi);
 };
@@ -81,12 +92,16 @@ struct ibx_stl {
 struct ibx_dfield {
   std::shared_ptr<ibx_stl> stl;
   std::vector<double> centers;  // ns x nd
+  double rmax = 0;              // largest centre-to-vertex distance over all simplices (upper bound, see projection)
   ibx::KDTree tree;
   // analytic sphere alternative (stl == nullptr)
   bool sphere = false;
   double sc[3] = {0, 0, 0};
   double sr = 0;
   ibx::Num distance(const double* x, bool xf32) const;
+  // distance(x) if it is <= r (evaluated like distance(), compared like `distance(x) <= r`), else false -- without paying
+  // for an exact nearest-neighbour search when x is far from the surface
+  bool distance_within(const double* x, bool xf32, double r, ibx::Num* out) const;
   // projection (src/mesher.jl:778-801); result in the promoted type
   void projection(const double* x, bool xf32, double R, double* out) const;
 };
@@ -139,6 +154,7 @@ struct BoundaryT {
   std::vector<int32_t> image_domain;
   std::vector<int32_t> ptr, idx;  // idx into image_domain
   std::vector<float> w;
+  int64_t n_tied = 0;  // ghosts whose k-th and (k+1)-th nearest donor candidates are exactly equidistant (tie rule applies)
   // device copies (idx_global = image_domain[idx])
   int32_t *d_ghost = nullptr, *d_ptr = nullptr, *d_idx_global = nullptr, *d_image_domain = nullptr, *d_idx = nullptr;
   float *d_w = nullptr, *d_normals = nullptr /* G x nd col-major */, *d_eta = nullptr;

@@ -334,12 +334,8 @@ template <int FLUX, int SEG, int HYB, bool X2, bool SHARE, bool HLR>
 int launch_march(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, ibx_fluid f, const float* P, const float* S,
                  float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st) {
   using C = MarchCfg<SEG>;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr = true;
-  }
+  int rc;
+  if ((rc = ensure_dyn_smem(c, (const void*)k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR>, C::SMEM))) return rc;
   k_march_flux<FLUX, SEG, HYB, X2, SHARE, HLR><<<n, C::NT, C::SMEM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;

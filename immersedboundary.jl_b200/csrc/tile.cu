@@ -557,14 +557,9 @@ template <int ND, int BS, bool P2>
 int launch_reg(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* P, const float* S, float* R, float* cfl) {
   using C = RegCfg<ND, BS>;
   if (D.n_own_regular == 0) return IBX_OK;
-  static bool attr = false;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CU(cudaFuncSetAttribute(k_reg_flux<ND, BS, P2, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr = true;
-  }
+  int rc;
+  if ((rc = ensure_dyn_smem(c, (const void*)k_reg_flux<ND, BS, P2, 0>, C::SMEM))) return rc;
+  if ((rc = ensure_dyn_smem(c, (const void*)k_reg_flux<ND, BS, P2, 1>, C::SMEM))) return rc;
   if (flux_kind == 0)
     k_reg_flux<ND, BS, P2, 0><<<D.n_own_regular, C::NT, C::SMEM, c->stream>>>(D.d_blk_own_regular, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
   else
@@ -1094,13 +1089,9 @@ int launch_hyb_mode(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int 
                     float* R, float* cfl, double* GF, float* GC, cudaStream_t st = nullptr) {
   using C = HybCfg<ND, BS, FINER>;
   if (!st) st = c->stream;
-  static bool attr = false;
   constexpr size_t SM = MODE == 1 ? C::SMEM_GENERAL : C::SMEM;
-  if (!attr) {
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM));
-    CU(cudaFuncSetAttribute(k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr = true;
-  }
+  int rc;
+  if ((rc = ensure_dyn_smem(c, (const void*)k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE>, SM))) return rc;
   k_hyb_flux<ND, BS, FINER, P2, FLUX, MODE><<<n, C::NT, SM, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl, GF, GC);
   LAUNCH_CHECK();
   return IBX_OK;
@@ -1208,25 +1199,19 @@ int launch_pair(ibx_ctx* c, const ibx_domain& D, const int32_t* sens_blocks, int
   using C = Cfg<ND, BS, FINER>;
   if (stage == 0) {
     if (n_sens == 0) return IBX_OK;
-    static bool attr = false;
-    if (!attr && C::SMEM_SENSOR > 48 * 1024) {
-      CU(cudaFuncSetAttribute(k_tile_sensor<ND, BS, FINER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_SENSOR));
-      CU(cudaFuncSetAttribute(k_tile_sensor<ND, BS, FINER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_SENSOR));
-      attr = true;
+    int rc;
+    if (C::SMEM_SENSOR > 48 * 1024) {
+      if ((rc = ensure_dyn_smem(c, (const void*)k_tile_sensor<ND, BS, FINER, true>, C::SMEM_SENSOR))) return rc;
+      if ((rc = ensure_dyn_smem(c, (const void*)k_tile_sensor<ND, BS, FINER, false>, C::SMEM_SENSOR))) return rc;
     }
     if (D.all_pow2) k_tile_sensor<ND, BS, FINER, true><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
     else k_tile_sensor<ND, BS, FINER, false><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
     LAUNCH_CHECK();
   } else {
     if (n_flux == 0) return IBX_OK;
-    static bool attr = false;
-    if (!attr) {
-      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FLUX));
-      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_FLUX));
-      CU(cudaFuncSetAttribute(k_tile_flux<ND, BS, FINER, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      attr = true;
-    }
+    int rc;
+    if ((rc = ensure_dyn_smem(c, (const void*)k_tile_flux<ND, BS, FINER, 0>, C::SMEM_FLUX))) return rc;
+    if ((rc = ensure_dyn_smem(c, (const void*)k_tile_flux<ND, BS, FINER, 1>, C::SMEM_FLUX))) return rc;
     if (flux_kind == 0)
       k_tile_flux<ND, BS, FINER, 0><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
     else

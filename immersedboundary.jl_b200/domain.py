@@ -335,6 +335,13 @@ class Boundary:
         return len(self.ghost_indices)
 
     @property
+    def n_tied(self):
+        """Ghosts whose k-th / (k+1)-th donor candidates are exactly equidistant (``ibx_boundary_tie_count``)."""
+        t = C.c_int64()
+        call("ibx_boundary_tie_count", self.dom._h, self.b, self.part, C.byref(t))
+        return t.value
+
+    @property
     def normals(self):
         """Device copy (nghost x nd) for BC closures."""
         out = DeviceArray(self.nghost, self.dom.ndims, False)
@@ -483,7 +490,28 @@ class Domain:
             for peer in range(nranks):
                 ids = np.ascontiguousarray(everyone[peer][rank], dtype=I32)
                 call("ibx_shard_set_send", loc._h, peer, len(ids), ptr(ids))
+            loc.shard_info["coupled_families"] = loc._coupled_families(all_gather_object)
         return loc
+
+    def _coupled_families(self, all_gather_object):
+        """Ordered pairs (e, l) of boundary families such that, on some rank, a ghost of family l interpolates from a
+        cell owned by ANOTHER rank that is a ghost of family e there.  The reference applies its ``impose_bc!`` calls
+        one after the other on one array, so family l must see family e's new values: ``ghost_update_euler`` exchanges
+        the halo rows between two such families (within one family the update is Jacobi: all reads before any write)."""
+        info = self.shard_info
+        l2g, n_owned = info["local_to_global"], info["n_owned"]
+        halo_donors, mine = {}, {}
+        for name, chunks in self.boundaries.items():
+            d = np.concatenate([b.image_domain for b in chunks.values()] or [np.zeros(0, I32)])
+            halo_donors[name] = np.unique(l2g[d[d >= n_owned]])
+            mine[name] = np.unique(l2g[np.concatenate([b.ghost_indices for b in chunks.values()] or [np.zeros(0, I32)])])
+        pairs = set()
+        for peer, theirs in enumerate(all_gather_object(halo_donors)):
+            if peer == info["rank"]:
+                continue
+            for l, ids in theirs.items():
+                pairs |= {(e, l) for e, g in mine.items() if e != l and len(ids) and np.isin(ids, g, assume_unique=True).any()}
+        return set().union(*all_gather_object(sorted(pairs)))
 
     def halo_exchange(self, a):
         """Post and complete the exchange of the halo rows of device array ``a`` (n_owned + n_halo rows)."""

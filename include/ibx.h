@@ -149,6 +149,10 @@ int ibx_partition_face_lists(const ibx_domain* d, int p, int dim, int side, int3
 /* boundaries (src/ImmersedBoundary.jl:406-476): boundary b has nparts chunks of <= max_partition_size ghosts */
 int ibx_boundary_name(const ibx_domain* d, int b, const char** name, int* nparts);
 int ibx_boundary_info(const ibx_domain* d, int b, int part, int64_t* nghost, int64_t* n_image_domain, int64_t* nnz);
+/* ghosts of the chunk whose k-th and (k+1)-th nearest donor candidates are exactly equidistant from the image point: the
+ * only ghosts where NearestNeighbors.jl's traversal-order tie-break (nninterp.jl:121-123; not reproducible)
+ * could pick a different donor than this library's documented (distance, lower index) rule */
+int ibx_boundary_tie_count(const ibx_domain* d, int b, int part, int64_t* n_tied);
 int ibx_boundary_tables(const ibx_domain* d, int b, int part, int32_t* ghost_indices, float* projections,
                         float* normals, float* image_distances, float* ghost_distances, int32_t* image_domain,
                         int32_t* interp_ptr, int32_t* interp_idx /* into image_domain */, float* interp_w);

@@ -90,7 +90,7 @@ static inline void p2s_point(float R, float gamma, int nd, const float* P, float
 }
 
 /* one partition: Qd (n_dom x nv, gathered) -> Rd, cd (n_dom) */
-static void residual_partition(const ibxref_part* p, int nd, float Rg, float gamma, const float* Qd, float* Rd, float* cd) {
+static void residual_partition(const ibxref_part* p, int nd, float Rg, float gamma, const float* Qd, float* Rd, float* cd, int use_sensor) {
   const int nv = nd + 2;
   const int64_t n = p->n_dom;
   int64_t nfmax = 0;
@@ -158,6 +158,11 @@ static void residual_partition(const ibxref_part* p, int nd, float Rg, float gam
         float gu = (2.0f * du[o] - gf) * down, Du = (2.0f * du[q] - gf) * dnei;
         float s = fminf(fabsf(Du), fabsf(gu)) * (sgnf(Du) + sgnf(gu)) / 2.0f;
         float l = uo + s, r = un - s;
+        if (!use_sensor) { /* MUSCL(...; D = nothing): no blend (src/ImmersedBoundary.jl:1141) */
+          PL[(int64_t)v * nf + f] = l;
+          PR[(int64_t)v * nf + f] = r;
+          continue;
+        }
         float Df = fmaxf(fmaxf(D[o], D[q]), 1e-7f);
         float ufc = (uo * dnei + un * down) / (down + dnei);
         PL[(int64_t)v * nf + f] = l * Df + (1.0f - Df) * ufc;
@@ -205,8 +210,8 @@ static void residual_partition(const ibxref_part* p, int nd, float Rg, float gam
 }
 
 /* dom(f, Q, R, cfl): one task per partition, gather -> residual -> scatter of the image rows */
-int ibxref_residual(int nparts, const ibxref_part* parts, int nd, float Rg, float gamma, int64_t N, const float* Q, float* R,
-                    float* cfl, int nthreads) {
+int ibxref_residual_ex(int nparts, const ibxref_part* parts, int nd, float Rg, float gamma, int64_t N, const float* Q, float* R,
+                       float* cfl, int nthreads, int use_sensor) {
   const int nv = nd + 2;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -220,7 +225,7 @@ int ibxref_residual(int nparts, const ibxref_part* parts, int nd, float Rg, floa
     float* cd = malloc(sizeof(float) * n);
     for (int v = 0; v < nv; ++v)
       for (int64_t i = 0; i < n; ++i) Qd[(int64_t)v * n + i] = Q[(int64_t)v * N + p->domain[i]];
-    residual_partition(p, nd, Rg, gamma, Qd, Rd, cd);
+    residual_partition(p, nd, Rg, gamma, Qd, Rd, cd, use_sensor);
     for (int64_t k = 0; k < p->n_img; ++k) {
       int64_t g = p->image[k], l = p->image_in_domain[k];
       for (int v = 0; v < nv; ++v) R[(int64_t)v * N + g] = Rd[(int64_t)v * n + l];
@@ -229,6 +234,11 @@ int ibxref_residual(int nparts, const ibxref_part* parts, int nd, float Rg, floa
     free(Qd); free(Rd); free(cd);
   }
   return 0;
+}
+
+int ibxref_residual(int nparts, const ibxref_part* parts, int nd, float Rg, float gamma, int64_t N, const float* Q, float* R,
+                    float* cfl, int nthreads) {
+  return ibxref_residual_ex(nparts, parts, nd, Rg, gamma, N, Q, R, cfl, nthreads, 1);
 }
 
 /* FlowBC(P, normals) at one point (src/cfd.jl:243-300, no wall-shear scaling) */

@@ -51,6 +51,8 @@ def lib():
         _lib = C.CDLL(build())
         _lib.ibxref_residual.restype = C.c_int
         _lib.ibxref_residual.argtypes = [C.c_int, C.POINTER(_Part), C.c_int, C.c_float, C.c_float, C.c_int64, PF, PF, PF, C.c_int]
+        _lib.ibxref_residual_ex.restype = C.c_int
+        _lib.ibxref_residual_ex.argtypes = [C.c_int, C.POINTER(_Part), C.c_int, C.c_float, C.c_float, C.c_int64, PF, PF, PF, C.c_int, C.c_int]
         _lib.ibxref_ghost_update.restype = C.c_int
         _lib.ibxref_ghost_update.argtypes = [C.c_int, C.POINTER(_Bdry), C.c_int, C.c_float, C.c_float, C.c_int64, PF, C.c_int]
     return _lib
@@ -145,11 +147,33 @@ class CpuRef:
             bd[name] = out
         return cls(nd, len(dom), parts, bd)
 
-    def residual(self, fluid, Q, R, cfl, n_threads=0):
-        """``dom(f, Q, R, cfl)`` with f = the canonical Euler residual (HLL); Q, R column-major (N, nv) float32."""
+    @classmethod
+    def from_dump(cls, path):
+        """Tables written by ``tools/dump_cpu_tables.py`` (a separate, untimed process runs the host-side builder, so the
+        process that times this CPU path never loads the product library).  Returns (CpuRef, Q0 column-major, meta)."""
+        import json
+        meta = json.load(open(os.path.join(path, "meta.json")))
+        ld = lambda name: np.load(os.path.join(path, name + ".npy"), mmap_mode="r")
+        nd = meta["nd"]
+        parts = []
+        for tag in meta["parts"]:
+            parts.append(dict(domain=ld(tag + "_domain"), image=ld(tag + "_image"), image_in_domain=ld(tag + "_iid"),
+                              spacing=ld(tag + "_spacing").T,
+                              faces={d: (ld(f"{tag}_own{d}"), ld(f"{tag}_nei{d}")) for d in range(nd)},
+                              lists={(d, side): (ld(f"{tag}_ptr{d}{int(side)}"), ld(f"{tag}_idx{d}{int(side)}"))
+                                     for d in range(nd) for side in (False, True)}))
+        bd = {name: [dict(ghost=ld(t + "_ghost"), image_domain=ld(t + "_imdom"), ptr=ld(t + "_ptr"), idx=ld(t + "_idx"),
+                          w=ld(t + "_w"), normals=ld(t + "_normals").T, eta=ld(t + "_eta")) for t in tags]
+              for name, tags in meta["boundaries"].items()}
+        Q = np.array(ld("Q")).T     # (N, nv) column-major, writable copy
+        return cls(nd, meta["ncells"], parts, bd), Q, meta
+
+    def residual(self, fluid, Q, R, cfl, n_threads=0, use_sensor=True):
+        """``dom(f, Q, R, cfl)`` with f = the canonical Euler residual (HLL); Q, R column-major (N, nv) float32.
+        ``use_sensor=False``: MUSCL without the ``D`` blend (``D = nothing``, src/ImmersedBoundary.jl:1141)."""
         assert Q.flags.f_contiguous and R.flags.f_contiguous and Q.dtype == F32 and R.dtype == F32 and cfl.dtype == F32
-        rc = lib().ibxref_residual(len(self.parts), self.parts, self.nd, float(fluid.R), float(fluid.gamma), self.N, _pf(Q), _pf(R),
-                                   _pf(cfl), int(n_threads))
+        rc = lib().ibxref_residual_ex(len(self.parts), self.parts, self.nd, float(fluid.R), float(fluid.gamma), self.N, _pf(Q), _pf(R),
+                                      _pf(cfl), int(n_threads), int(bool(use_sensor)))
         assert rc == 0
 
     def ghost_update(self, fluid, Q, bcs, n_threads=0):

@@ -241,9 +241,38 @@ def proj2simplex_batch(simp, pt):
     M = np.swapaxes(simp[:, 1:, :] - p0[:, None, :], 1, 2)  # (B, nd, nv-1)
     rhs = pt - p0
     dt = np.result_type(M.dtype, rhs.dtype)
-    xi = np.einsum("bij,bj->bi", pinv(M).astype(dt), rhs.astype(dt))
+    nd = simp.shape[2]
+    if nv == 3:
+        # Canonical rule: LinearAlgebra.pinv goes through LAPACK's SVD, which is neither vendored
+        # nor bit-reproducible.  For a full-rank nd x 2 matrix pinv(M) = (M^T M)^-1 M^T, evaluated in Float64 from the
+        # rounded entries of M (Gram sums in dimension order, closed-form 2 x 2 inverse) and rounded once; products and
+        # sums below are then taken one by one in the promoted type, like Julia's generic matvec.
+        M64 = M.astype(np.float64)
+        m0, m1 = M64[:, :, 0], M64[:, :, 1]
+        ga, gb, gc = m0[:, 0] * m0[:, 0], m0[:, 0] * m1[:, 0], m1[:, 0] * m1[:, 0]
+        for d in range(1, nd):
+            ga, gb, gc = ga + m0[:, d] * m0[:, d], gb + m0[:, d] * m1[:, d], gc + m1[:, d] * m1[:, d]
+        det = ga * gc - gb * gb
+        ok = det > 1e-10 * (ga * gc)
+        with np.errstate(all="ignore"):
+            P0 = (gc[:, None] * m0 - gb[:, None] * m1) / det[:, None]
+            P1 = (ga[:, None] * m1 - gb[:, None] * m0) / det[:, None]
+        Pm = np.stack([P0, P1], axis=1)                       # (B, 2, nd)
+        if not ok.all():
+            Pm[~ok] = pinv(M[~ok]).astype(np.float64)
+        Pm = Pm.astype(M.dtype).astype(dt)
+        r_, Mt = rhs.astype(dt), M.astype(dt)
+        xi = np.zeros((len(simp), 2), dtype=dt)
+        for j in range(2):
+            acc = Pm[:, j, 0] * r_[:, 0]
+            for d in range(1, nd):
+                acc = acc + Pm[:, j, d] * r_[:, d]
+            xi[:, j] = acc
+        res = p0.astype(dt) + (Mt[:, :, 0] * xi[:, 0:1] + Mt[:, :, 1] * xi[:, 1:2])
+    else:
+        xi = np.einsum("bij,bj->bi", pinv(M).astype(dt), rhs.astype(dt))
+        res = (p0.astype(dt) + np.einsum("bij,bj->bi", M.astype(dt), xi))
     inside = ~(np.any(xi < -eps, axis=1) | (np.sum(xi, axis=1) > 1.0 + eps))
-    res = (p0.astype(dt) + np.einsum("bij,bj->bi", M.astype(dt), xi))
     out_idx = np.flatnonzero(~inside)
     if out_idx.size:
         best = np.zeros((out_idx.size, simp.shape[2]), dtype=dt)

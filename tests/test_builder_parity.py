@@ -70,7 +70,9 @@ def test_tables_3d_analytic_sphere(get_case):
 
 
 def test_tables_3d_stl_sphere(get_case):
-    _check_tables(get_case("sphere3d_stl", 100_000), donors_exact=False)
+    """3-D STL surface (triangle projection, src/mesher.jl:544-596): ghost set, projections, normals, image points and
+    donor sets bit-exact (the canonical Float64 pseudo-inverse rule of DESIGN.md section 2 on both sides)."""
+    _check_tables(get_case("sphere3d_stl", 100_000), donors_exact=True)
 
 
 def test_surfaces(get_case):

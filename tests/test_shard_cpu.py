@@ -103,3 +103,43 @@ def test_single_rank_shard_is_identity(ib):
     assert np.array_equal(loc.block_faces(), g.block_faces())
     for name in g.boundaries:
         assert sum(b.nghost for b in loc.boundaries[name].values()) == sum(b.nghost for b in g.boundaries[name].values())
+
+
+def _shard_all(ib, msh, fams, world):
+    """Every rank's shard in one process: threads with a barrier stand in for all_gather_object (ctypes drops the GIL)."""
+    import threading
+    g = ib.Domain(msh, hypercube_families=fams, build_partitions=False, upload=False)
+    bar, slots, out = threading.Barrier(world), [None] * world, [None] * world
+
+    def worker(r):
+        def gather(obj):
+            slots[r] = obj
+            bar.wait()
+            res = list(slots)
+            bar.wait()
+            return res
+        out[r] = g.shard(r, world, all_gather_object=gather).shard_info
+
+    ts = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return out
+
+
+def test_boundary_families_coupled_across_ranks_are_detected(ib):
+    """ghost_update_euler applies the families in sequence; when a ghost of one family interpolates from a ghost of
+    another family owned by a different rank, the halo rows must be refreshed in between.  A body far from
+    the box needs no extra exchange, a body next to a box face does -- and every rank must agree (the exchange is
+    collective)."""
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    far = ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(0.12)),
+                  refinement_regions=[(ib.Ball([0, 0, 0], 0.9), F32(0.24))])
+    close = ib.Mesh([-1, -1, -1], [2, 2, 2], ("wall", ib.Sphere([-0.55, 0, 0], 0.4), F32(0.1)),
+                    refinement_regions=[(ib.Ball([-0.55, 0, 0], 0.6), F32(0.1))])
+    for world in (2, 4):
+        assert all(i["coupled_families"] == set() for i in _shard_all(ib, far, fams, world))
+        infos = _shard_all(ib, close, fams, world)
+        assert all(i["coupled_families"] == infos[0]["coupled_families"] for i in infos)
+        assert ("farfield", "wall") in infos[0]["coupled_families"] or ("wall", "farfield") in infos[0]["coupled_families"]

@@ -1,5 +1,10 @@
-"""Multi-GPU parity check (run under torchrun): the sharded step (halo exchange over NCCL + ghost update + residual)
-must reproduce, on every rank's owned cells, the single-domain result computed on the same GPU."""
+"""Multi-GPU parity worker (run under torchrun; tests/test_mgpu_gpu.py launches it for 2 / 4 / 8 ranks): the sharded step
+(halo exchange over NCCL + ghost update + halo exchange + residual) must reproduce, on every rank's owned cells, the
+single-domain result computed on the same GPU -- bit for bit.
+
+Cases: `sphere` (body far from the box: the two boundary families do not interact) and `close` (a sphere next to a box
+face: wall ghosts interpolate from farfield ghosts owned by other ranks, so ghost_update_euler has to exchange the halo
+rows between the two families -- ADVICE r1)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,9 +18,6 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = ib.context(local)
 fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
-msh = ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(0.06)),
-              refinement_regions=[(ib.Ball([0, 0, 0], 0.9), F32(0.12))])
-g = ib.Domain(msh, hypercube_families=fams, build_partitions=False, upload=False)
 
 
 def gather(obj):
@@ -24,7 +26,6 @@ def gather(obj):
     return out
 
 
-loc = g.shard(rank, world, all_gather_object=gather)
 ident = np.zeros(128, np.uint8)
 if rank == 0:
     ib._lib.call("ibx_comm_unique_id", ib._lib.ptr(ident))
@@ -32,51 +33,63 @@ obj = [ident.tobytes()]
 dist.broadcast_object_list(obj, src=0)
 ident = np.frombuffer(obj[0], np.uint8).copy()
 ib._lib.call("ibx_comm_init", ctx, rank, world, ib._lib.ptr(ident))
-loc.upload()
-g.upload()
-info = loc.shard_info
-l2g, n_owned = info["local_to_global"], info["n_owned"]
 fl = ib.Fluid()
 a = np.sqrt(1.4 * 283.0 * 288.15)
 bcs = [("wall", ib.FlowBC(fl, np.array([101325.0, 288.15, 0.0], F32), normal_flow=True)),
        ("farfield", ib.FlowBC(fl, np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)))]
-Qg0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(g.cells()[0]))
-# reference: whole domain on this GPU
-Qg = ib.DeviceArray.from_host(Qg0)
-Rg, cg = ib.DeviceArray(len(g), 5, False), ib.DeviceArray(len(g), 1, True)
-for _ in range(2):
-    ib.ghost_update_euler(g, fl, Qg, bcs)
-    ib.residual_euler(g, fl, Qg, Rg, cg)
-# sharded: only the owned rows are initialised; halo rows arrive through the exchange
-Ql0 = np.zeros((len(loc), 5), F32)
-Ql0[:n_owned] = Qg0[l2g[:n_owned]]
-Ql = ib.DeviceArray.from_host(Ql0)
-Rl, cl = ib.DeviceArray(len(loc), 5, False), ib.DeviceArray(len(loc), 1, True)
-need = np.concatenate([v for v in info["requests"].values()])
-g2l = {int(gid): i for i, gid in enumerate(l2g)}
-need_local = np.array([g2l[int(x)] for x in need], dtype=np.int64)
-loc.halo_exchange(Ql)
-ib.synchronize()
-got = Ql.to_host()
-print(f"rank {rank}: after first exchange: needed rows correct = {np.array_equal(got[need_local], Qg0[need])}, "
-      f"zero rows among needed = {(np.abs(got[need_local]).sum(axis=1) == 0).sum()} of {len(need)}", flush=True)
-for _ in range(2):  # twice: the second pass sees ghost values updated (and exchanged) by the first
+
+
+def case(label, msh, expect_coupled):
+    g = ib.Domain(msh, hypercube_families=fams, build_partitions=False, upload=False)
+    loc = g.shard(rank, world, all_gather_object=gather)
+    loc.upload()
+    g.upload()
+    info = loc.shard_info
+    l2g, n_owned = info["local_to_global"], info["n_owned"]
+    Qg0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(g.cells()[0]))
+    # reference: whole domain on this GPU
+    Qg = ib.DeviceArray.from_host(Qg0)
+    Rg, cg = ib.DeviceArray(len(g), 5, False), ib.DeviceArray(len(g), 1, True)
+    for _ in range(2):
+        ib.ghost_update_euler(g, fl, Qg, bcs)
+        ib.residual_euler(g, fl, Qg, Rg, cg)
+    # sharded: only the owned rows are initialised; halo rows arrive through the exchange
+    Ql0 = np.zeros((len(loc), 5), F32)
+    Ql0[:n_owned] = Qg0[l2g[:n_owned]]
+    Ql = ib.DeviceArray.from_host(Ql0)
+    Rl, cl = ib.DeviceArray(len(loc), 5, False), ib.DeviceArray(len(loc), 1, True)
+    need = np.concatenate([v for v in info["requests"].values()])
+    g2l = {int(gid): i for i, gid in enumerate(l2g)}
+    need_local = np.array([g2l[int(x)] for x in need], dtype=np.int64)
     loc.halo_exchange(Ql)
-    ib.ghost_update_euler(loc, fl, Ql, bcs)
-    loc.halo_begin(Ql)      # completed inside residual_euler (overlapped with the owned-row conversion)
-    ib.residual_euler(loc, fl, Ql, Rl, cl)
-own = l2g[:n_owned]
-okR = np.array_equal(Rl.to_host()[:n_owned], Rg.to_host()[own])
-okc = np.array_equal(cl.to_host()[:n_owned], cg.to_host()[own])
-okQ = np.array_equal(Ql.to_host()[:n_owned], Qg.to_host()[own])
-dR = np.abs(Rl.to_host()[:n_owned] - Rg.to_host()[own]).max(axis=1)
-dQ = np.abs(Ql.to_host()[:n_owned] - Qg.to_host()[own]).max(axis=1)
-print(f"rank {rank}: cells with R mismatch {(dR > 0).sum()}, Q mismatch {(dQ > 0).sum()}; first bad R cells {np.flatnonzero(dR > 0)[:10]}, bad Q {np.flatnonzero(dQ > 0)[:10]}", flush=True)
-print(f"rank {rank}: owned {n_owned} halo {info['n_halo']} exchanged {len(need)} | Q {okQ} R {okR} cfl {okc}", flush=True)
-t = torch.tensor([int(okR and okc and okQ)], device="cuda")
-dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ib.synchronize()
+    got = Ql.to_host()
+    ok0 = np.array_equal(got[need_local], Qg0[need])
+    for _ in range(2):  # twice: the second pass sees ghost values updated (and exchanged) by the first
+        loc.halo_exchange(Ql)
+        ib.ghost_update_euler(loc, fl, Ql, bcs)
+        loc.halo_begin(Ql)      # completed inside residual_euler (overlapped with compute on the owned rows)
+        ib.residual_euler(loc, fl, Ql, Rl, cl)
+    own = l2g[:n_owned]
+    okR = np.array_equal(Rl.to_host()[:n_owned], Rg.to_host()[own])
+    okc = np.array_equal(cl.to_host()[:n_owned], cg.to_host()[own])
+    okQ = np.array_equal(Ql.to_host()[:n_owned], Qg.to_host()[own])
+    dR = np.abs(Rl.to_host()[:n_owned] - Rg.to_host()[own]).max(axis=1)
+    coupled = sorted(info.get("coupled_families", ()))
+    print(f"[{label}] rank {rank}: owned {n_owned} halo {info['n_halo']} exchanged {len(need)} coupled {coupled} | first exchange {ok0} "
+          f"Q {okQ} R {okR} cfl {okc} (cells with R mismatch {(dR > 0).sum()})", flush=True)
+    ok = ok0 and okR and okc and okQ and (bool(coupled) == expect_coupled)
+    t = torch.tensor([int(ok)], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return t.item() == 1
+
+
+ok = case("sphere", ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(0.06)),
+                            refinement_regions=[(ib.Ball([0, 0, 0], 0.9), F32(0.12))]), False)
+ok &= case("close", ib.Mesh([-1, -1, -1], [2, 2, 2], ("wall", ib.Sphere([-0.55, 0, 0], 0.4), F32(0.05)),
+                           refinement_regions=[(ib.Ball([-0.55, 0, 0], 0.6), F32(0.05))]), True)
 ib._lib.call("ibx_comm_finalize", ctx)
 dist.destroy_process_group()
 if rank == 0:
-    print("MGPU PARITY", "OK" if t.item() == 1 else "FAILED", flush=True)
-sys.exit(0 if t.item() == 1 else 1)
+    print("MGPU PARITY", "OK" if ok else "FAILED", flush=True)
+sys.exit(0 if ok else 1)
