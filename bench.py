@@ -127,6 +127,23 @@ class ClockSampler:
                 "samples": len(sm), "samples_total": len(self.rows), "reasons": reasons, "how": "NVML polled every ~5 ms during the timed region"}
 
 
+def flux_scaled_error(dom_cells_widths, Q, R, R_ref, gamma=1.4, Rgas=283.0):
+    """|r - r_ref| / max(|r_ref|, sum_faces |F| / dx) per cell and variable, with the face-flux
+    magnitude estimated from the cell state (|F| of the physical flux in each direction, two faces per direction)."""
+    Q = Q.astype(np.float64)
+    nd = Q.shape[1] - 2
+    rho, E = Q[:, 0], Q[:, 1]
+    u = Q[:, 2:] / rho[:, None]
+    p = (gamma - 1.0) * (E - 0.5 * rho * (u ** 2).sum(axis=1))
+    S = np.zeros_like(Q)
+    for d in range(nd):
+        F = Q * u[:, d:d + 1]
+        F[:, 1] += p * u[:, d]
+        F[:, 2 + d] += p
+        S += 2.0 * np.abs(F) / dom_cells_widths[:, d:d + 1].astype(np.float64)
+    return np.abs(R.astype(np.float64) - R_ref) / np.maximum(np.abs(R_ref.astype(np.float64)), S)
+
+
 def measured_peak_gbs():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"

@@ -8,7 +8,7 @@ from ._lib import IbxError  # noqa: F401
 from .mesher import (Stereolitography, merge_points, refine_to_length, feature_regions, centers_and_normals,  # noqa: F401
                      Ball, Box, Line, Sphere, DistanceField, Mesh, get_cells)
 from .domain import (Domain, Partition, Boundary, Surface, DeviceArray, Accumulator, Interpolator, context,  # noqa: F401
-                     synchronize, launch_count, maximum, minimum, dot, at_owners, at_neighbors, at_faces, green_gauss,
+                     synchronize, launch_count, set_option, get_option, options, maximum, minimum, dot, at_owners, at_neighbors, at_faces, green_gauss,
                      unsigned_green_gauss, divergent, cell_gradient, face_distance, owner_distance, neighbor_distance,
                      face_gradient, JST_sensor, MUSCL, impose_bc, multigrid, volume_integral, surface_integral,
                      at_offset)

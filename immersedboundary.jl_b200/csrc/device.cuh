@@ -17,6 +17,8 @@ struct ibx_ctx {
   int64_t launches = 0;
   int64_t halo_pending = 0;   // array handle of a posted, not yet completed halo exchange (ibx_halo_begin / _end)
   bool poisoned = false;
+  // run-time options of the fused residual (ibx_set_option): code path, arithmetic, sensor blend
+  int opt_path = 0, opt_arith = 0, opt_sensor = 1;
   struct Arr { float* p; int64_t rows, cols; bool f64; };  // f64: the buffer holds doubles (HLL fluxes, src/cfd.jl:504-507)
   std::unordered_map<int64_t, Arr> arrays;
   int64_t next_handle = 1;
@@ -63,6 +65,9 @@ int sensor_regular(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n
 bool march_supported(const ibx_domain& D);
 int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,
                const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st);
+// the same pass with option "arithmetic" = 1 (march_fast.cu)
+int march_flux_fast(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,
+                    const float* S, float* R, float* cfl, const double* GF, const float* GC, cudaStream_t st);
 
 #define CU(call)                                                                      \
   do {                                                                                \

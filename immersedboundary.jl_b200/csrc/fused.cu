@@ -484,10 +484,11 @@ int ibx_residual_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_ki
   if (!scratch) return fail(IBX_ERR_CUDA, "ibx_residual_euler: out of device memory for the primitive/sensor scratch");
   float* P = scratch;
   float* S = scratch + N * nv;
-  // tile kernels (one CTA per block, shared-memory staging) for power-of-two blocks; IBX_GENERIC=1 forces the
-  // gather kernels (kept as the fallback for other block sizes and as a cross-check)
-  const bool force_generic = getenv("IBX_GENERIC") != nullptr;
-  const bool tiles = tile_supported(D) && !force_generic;
+  // tile / marching kernels (one CTA per block, shared-memory staging) for block sizes 8, 4, 2; option "path" = 2 forces
+  // the per-cell gather kernels below (the fallback for other block sizes, and an independent cross-check)
+  const bool tiles = tile_supported(D) && c->opt_path != 2;
+  if (!tiles && (c->opt_arith != 0 || c->opt_sensor != 1))
+    return fail(IBX_ERR_UNSUPPORTED, "ibx_residual_euler: the gather kernels implement arithmetic = 0 and sensor = 1 only");
   // a posted halo exchange (ibx_halo_begin without ibx_halo_end): the tile path overlaps it with the conversion of the
   // owned rows when it is Q's; anything else waits for it here
   if (c->halo_pending && (!tiles || c->halo_pending != Qh)) {

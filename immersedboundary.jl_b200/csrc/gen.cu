@@ -3,7 +3,7 @@
 // block whose 4-cell stencil leaves the uniform lattice.  They are 2.5 % of the faces of the C4 mesh; the generic
 // neighbour-list code that used to evaluate them (k_hyb_flux MODE 1, tile.cu) took 17 % of the step.
 //
-// One CTA per irregular block, one thread per pencil of the irregular face; no shared memory, no barrier: a thread
+// One CTA per irregular block, one thread per pencil of an irregular face (64 per dimension); no shared memory, no barrier: a thread
 // reads the three own cells behind the face and the halo cells in front of it straight from global memory (each is
 // read by at most four threads; L1 absorbs that) and evaluates, with the arithmetic and the operation order of the
 // reference (weights 1/len, products first, sums in list order: src/accumulator.jl:95-106, at_faces :899-910,
@@ -42,16 +42,18 @@ __device__ __forceinline__ void face_flux(ibx_fluid fl, int d, const CellVals& O
   const bool fast = ho == hn;
   muscl_face<NV>(O.u, Nn.u, go, gn, ho, hn, O.u[NV], Nn.u[NV], true, false, pl, pr, fast);
   double F_[NV];
+  // the in-range division / square-root sequences (physics.cuh): same bits as the guarded library forms for pressures,
+  // R T and gamma R T, without their range-check branches
   if (FLUX == 0) {
-    hll_flux<ND>(fl, pl, pr, d, F_);
+    hll_flux<ND, true>(fl, pl, pr, d, F_);
   } else {
     float Ff[NV];
-    rusanov_flux<ND>(fl, pl, pr, face_interp(O.u[NV], Nn.u[NV], ho, hn), d, Ff);
+    rusanov_flux<ND, true>(fl, pl, pr, face_interp(O.u[NV], Nn.u[NV], ho, hn), d, Ff);
 #pragma unroll
     for (int v = 0; v < NV; ++v) F_[v] = (double)Ff[v];
   }
   const float gr = fl.gamma * fl.R;
-  const float ao = sqrtf(gr * clampT(O.u[1])), an = sqrtf(gr * clampT(Nn.u[1]));
+  const float ao = sqrt_rn_inrange(gr * clampT(O.u[1])), an = sqrt_rn_inrange(gr * clampT(Nn.u[1]));
   const float ct = fabsf(face_interp_f(pick<ND>(O.u + 2, d), pick<ND>(Nn.u + 2, d), ho, hn, fast)) + face_interp_f(ao, an, ho, hn, fast);
 #pragma unroll
   for (int v = 0; v < NV; ++v) GF[slot * NV + v] = F_[v];
@@ -59,15 +61,16 @@ __device__ __forceinline__ void face_flux(ibx_fluid fl, int d, const CellVals& O
 }
 
 template <int FLUX, bool FINER>
-__global__ void __launch_bounds__(FACE)
+__global__ void __launch_bounds__(3 * FACE)
 k_gen_faces(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
             ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, double* __restrict__ GF, float* __restrict__ GC) {
   constexpr int NX = FINER ? 2 * FACE * 4 : 0, NSL = 4 * FACE + NX;
   const int64_t b = blocks[blockIdx.x];
-  const int pen = threadIdx.x, t1 = pen & 7, t2 = pen >> 3;
+  // 192 threads: one group of 64 (one thread per pencil) per dimension, each walking the low and the high block face
+  const int grp = threadIdx.x >> 6, pen = threadIdx.x & 63, t1 = pen & 7, t2 = pen >> 3;
   const int64_t cell0 = b * CPB;
 #pragma unroll 1
-  for (int f = 0; f < 2 * ND; ++f) {
+  for (int f = 2 * grp; f < 2 * grp + 2; ++f) {
     const BlockFace bf = faces[b * (2 * ND) + f];
     if (bf.kind == 1) continue;
     const int d = f >> 1, side = f & 1;
@@ -318,11 +321,11 @@ int general_faces(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n,
                   const float* P, const float* S, double* GF, float* GC, cudaStream_t st) {
   if (n == 0) return IBX_OK;
   if (finer) {
-    if (flux_kind == 0) k_gen_faces<0, true><<<n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
-    else k_gen_faces<1, true><<<n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    if (flux_kind == 0) k_gen_faces<0, true><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    else k_gen_faces<1, true><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
   } else {
-    if (flux_kind == 0) k_gen_faces<0, false><<<n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
-    else k_gen_faces<1, false><<<n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    if (flux_kind == 0) k_gen_faces<0, false><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    else k_gen_faces<1, false><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
   }
   LAUNCH_CHECK();
   return IBX_OK;

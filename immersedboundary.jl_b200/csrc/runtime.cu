@@ -144,6 +144,33 @@ int ibx_device_info(ibx_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int
   return IBX_OK;
 }
 
+static int* option_slot(ibx_ctx* c, const char* name, int* lo, int* hi) {
+  std::string n = name ? name : "";
+  if (n == "path") { *lo = 0; *hi = 2; return &c->opt_path; }
+  if (n == "arithmetic") { *lo = 0; *hi = 1; return &c->opt_arith; }
+  if (n == "sensor") { *lo = 0; *hi = 1; return &c->opt_sensor; }
+  return nullptr;
+}
+
+int ibx_set_option(ibx_ctx* c, const char* name, int value) {
+  CHECK_CTX(c);
+  int lo, hi;
+  int* slot = option_slot(c, name, &lo, &hi);
+  if (!slot) return fail(IBX_ERR_ARG, std::string("ibx_set_option: unknown option '") + (name ? name : "") + "' (path, arithmetic, sensor)");
+  if (value < lo || value > hi) return fail(IBX_ERR_ARG, std::string("ibx_set_option: value out of range for '") + name + "'");
+  *slot = value;
+  return IBX_OK;
+}
+
+int ibx_get_option(ibx_ctx* c, const char* name, int* value) {
+  CHECK_CTX(c);
+  int lo, hi;
+  int* slot = option_slot(c, name, &lo, &hi);
+  if (!slot) return fail(IBX_ERR_ARG, std::string("ibx_get_option: unknown option '") + (name ? name : "") + "'");
+  *value = *slot;
+  return IBX_OK;
+}
+
 int ibx_launch_count(ibx_ctx* c, int64_t* out) {
   CHECK_CTX(c);
   *out = c->launches;

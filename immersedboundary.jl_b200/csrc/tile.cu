@@ -34,7 +34,6 @@ struct Cfg {
   static constexpr int NT = CPB >= 512 ? 256 : (CPB >= 64 ? 64 : 32);
   static constexpr int CPT = (CPB + NT - 1) / NT;
   // doubles first (8-byte alignment): face fluxes [NV][NG]; then floats: P [NV][NS], D [NS], CFL term [NG]
-  static constexpr size_t SMEM_FLUX = sizeof(double) * (size_t)NV * NG + sizeof(float) * ((size_t)(NV + 1) * NS + (size_t)NG);
   static constexpr size_t SMEM_SENSOR = sizeof(float) * ((size_t)CPB + NFACES * MAXL1);
 };
 
@@ -105,294 +104,6 @@ k_tile_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ 
       stride *= BS;
     }
     D[cell0 + l] = nu;
-  }
-}
-
-// ------------------------------------------------------------------------------------------ flux pass
-// Green-Gauss gradient along d of the NV staged variables at OWN cell l (src/ImmersedBoundary.jl:918-926, :965-972)
-template <int ND, int BS, bool FINER, int NV, int NS>
-__device__ __forceinline__ void own_grad(const float* __restrict__ sP, const FaceInfo& FL, const FaceInfo& FH, int l,
-                                         const int (&ii)[3], int d, int stride, float hd, bool p2, float inv_hd, float* g) {
-  float m[2][NV];
-#pragma unroll
-  for (int side = 0; side < 2; ++side) {
-    bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
-    if (inner) {
-      int n = side ? l + stride : l - stride;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + n], hd, hd, p2);
-    } else {
-      const FaceInfo& F = side ? FH : FL;
-      if (F.kind == 0) {  // box face: owner == neighbour == l
-#pragma unroll
-        for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + l], hd, hd, p2);
-      } else if (!FINER || F.kind != 3) {
-        int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
-        int n = F.base + (F.kind == 1 ? a2 * F.n1 + a1 : (a2 >> 1) * F.n1 + (a1 >> 1));
-        const bool ff = p2 && F.kind == 1;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) m[side][v] = face_interp_f(sP[v * NS + l], sP[v * NS + n], hd, F.hn, ff);
-      } else {
-        int slot[4];
-        int cnt = own_to_halo<ND, BS>(F, ii[T1(d)], ND == 3 ? ii[T2(d)] : 0, slot);
-        float w = 1.0f / (float)cnt;
-        for (int q = 0; q < cnt; ++q) {
-          int n = F.base + slot[q];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            float fv = face_interp(sP[v * NS + l], sP[v * NS + n], hd, F.hn);
-            m[side][v] = q == 0 ? fv * w : m[side][v] + fv * w;
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < NV; ++v) g[v] = p2 ? (m[1][v] - m[0][v]) * inv_hd : (m[1][v] - m[0][v]) / hd;
-}
-
-// gradient along d at halo cell r (layer 0) of face (d, side): far side = its layer-1 twin, near side = own cells
-template <int ND, int BS, bool FINER, int NV, int NS>
-__device__ __forceinline__ void halo_grad(const float* __restrict__ sP, const FaceInfo& F, int side, int r, int d, float hd,
-                                          bool p2, float* g) {
-  int j1 = r % F.n1, j2 = r / F.n1;
-  int n = F.base + r, far = n + F.n1 * F.n2;
-  float hc = F.hn;
-  int bnd = side ? BS - 1 : 0;
-  float nearv[NV], farv[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v) farv[v] = face_interp_f(sP[v * NS + n], sP[v * NS + far], hc, hc, p2);
-  if (F.kind == 1) {
-    int o = compose<ND, BS>(d, bnd, j1, j2);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) nearv[v] = face_interp_f(sP[v * NS + n], sP[v * NS + o], hc, hd, p2);
-  } else if (FINER && F.kind == 3) {
-    int o = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) nearv[v] = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
-  } else {  // coarser halo cell: 2^(ND-1) own fine cells face it, ascending cell id
-    constexpr int CNT = ND == 3 ? 4 : 2;
-    const float w = 1.0f / (float)CNT;
-#pragma unroll
-    for (int q = 0; q < CNT; ++q) {
-      int o = compose<ND, BS>(d, bnd, 2 * j1 + (q & 1), 2 * j2 + (q >> 1));
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        float fv = face_interp(sP[v * NS + n], sP[v * NS + o], hc, hd);
-        nearv[v] = q == 0 ? fv * w : nearv[v] + fv * w;
-      }
-    }
-  }
-  const float invc = 1.0f / hc;  // exact when p2 (hc = hd, 2 hd or hd / 2)
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    float df = side ? farv[v] - nearv[v] : nearv[v] - farv[v];
-    g[v] = p2 ? df * invc : df / hc;
-  }
-}
-
-template <int ND, int BS, bool FINER, int FLUX>
-__global__ void __launch_bounds__(Cfg<ND, BS, FINER>::NT, (ND == 3 && BS == 8 && !FINER) ? 3 : 1)
-k_tile_flux(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh,
-            int64_t N, ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg,
-            float* __restrict__ R, float* __restrict__ cfl) {
-  using C = Cfg<ND, BS, FINER>;
-  constexpr int NV = C::NV, CPB = C::CPB, NT = C::NT, NS = C::NS, NG = C::NG, MAXL1 = C::MAXL1;
-  extern __shared__ double smem_d[];
-  __shared__ FaceInfo fi[C::NFACES];
-  __shared__ float h[3];
-  double* sF = smem_d;                 // [NV][NG] face fluxes of the current dimension (Float64, see hll_flux)
-  float* sP = (float*)(sF + NV * NG);  // [NV][NS] primitives
-  float* sD = sP + NV * NS;            // [NS]     sensor
-  float* sC = sD + NS;                 // [NG]     CFL term of each face
-  const int64_t b = blocks[blockIdx.x];
-  const int tid = threadIdx.x;
-  if (tid < C::NFACES) fill_face_info<ND, BS>(fi[tid], faces[b * C::NFACES + tid], CPB + tid * 2 * MAXL1, bh[b * ND + (tid >> 1)]);
-  if (tid < ND) h[tid] = bh[b * ND + tid];
-  __syncthreads();
-  // ---- stage own cells (coalesced runs of CPB floats per variable) and the 2-layer halos
-  const int64_t cell0 = b * CPB;
-  for (int l = tid; l < CPB; l += NT) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) sP[v * NS + l] = P[(int64_t)v * N + cell0 + l];
-    sD[l] = Dg[cell0 + l];
-  }
-#pragma unroll
-  for (int f = 0; f < C::NFACES; ++f) {
-    const FaceInfo& F = fi[f];
-    if (F.kind == 0) continue;
-    int d = f >> 1, side = f & 1, n1n2 = F.n1 * F.n2;
-    for (int k = tid; k < 2 * n1n2; k += NT) {
-      int layer = k / n1n2, r = k - layer * n1n2;
-      int64_t c = halo_cell<ND, BS>(F, d, side, r % F.n1, r / F.n1, layer, CPB);
-      int s = F.base + k;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) sP[v * NS + s] = P[(int64_t)v * N + c];
-      sD[s] = Dg[c];
-    }
-  }
-  __syncthreads();
-
-  float res[C::CPT][NV], cf[C::CPT];
-#pragma unroll
-  for (int q = 0; q < C::CPT; ++q) {
-    cf[q] = 0.0f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) res[q][v] = 0.0f;
-  }
-  const float gr = fl.gamma * fl.R;
-
-  int stride = 1;
-#pragma unroll 1
-  for (int d = 0; d < ND; ++d) {
-    const float hd = h[d];
-    const bool p2 = is_pow2(hd);                 // exact fast paths (see physics.cuh) on same-spacing faces
-    const float inv_hd = 1.0f / hd;              // exact when p2
-    const double inv_hd_d = 1.0 / (double)hd;
-    const FaceInfo& FL = fi[2 * d];
-    const FaceInfo& FH = fi[2 * d + 1];
-    // ---- (1) face fluxes along d, each face once: internal faces (slot = owner cell), low face, high face.
-    //      Cell gradients (Green-Gauss along d) are formed on the fly from the staged primitives.
-    const int nfl = FL.nfaces, nfh = FH.nfaces;
-    for (int it = tid; it < CPB + nfl + nfh; it += NT) {
-      float po[NV], pn[NV], g0[NV], g1[NV];
-      float ho, hn, Do, Dn;
-      int fslot;
-      if (it < CPB) {
-        int ii[3];
-        split<ND, BS>(it, ii);
-        if (ii[d] == BS - 1) continue;
-        const int so = it, sn = it + stride;
-        own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, so, ii, d, stride, hd, p2, inv_hd, g0);
-        ii[d] += 1;
-        own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, sn, ii, d, stride, hd, p2, inv_hd, g1);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) { po[v] = sP[v * NS + so]; pn[v] = sP[v * NS + sn]; }
-        Do = sD[so]; Dn = sD[sn];
-        ho = hd; hn = hd; fslot = it;
-      } else {
-        const int side = it - CPB >= nfl ? 1 : 0;
-        const FaceInfo& F = side ? FH : FL;
-        const int k = it - CPB - (side ? nfl : 0);
-        const int bnd = side ? BS - 1 : 0;
-        int own, hs = -1, hr = 0;
-        if (FINER && F.kind == 3) {
-          int j1 = k % F.n1, j2 = k / F.n1;
-          own = compose<ND, BS>(d, bnd, j1 >> 1, j2 >> 1);
-          hr = k;
-        } else {
-          int a1 = k % BS, a2 = k / BS;
-          own = compose<ND, BS>(d, bnd, a1, a2);
-          hr = F.kind == 1 ? k : (a2 >> 1) * F.n1 + (a1 >> 1);
-        }
-        int ii[3];
-        split<ND, BS>(own, ii);
-        float gown[NV], ghal[NV], pown[NV], phal[NV];
-        own_grad<ND, BS, FINER, NV, NS>(sP, FL, FH, own, ii, d, stride, hd, p2, inv_hd, gown);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) pown[v] = sP[v * NS + own];
-        float Down = sD[own], Dhal, hh;
-        if (F.kind == 0) {  // box face: both sides are the own cell
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { phal[v] = pown[v]; ghal[v] = gown[v]; }
-          Dhal = Down; hh = hd;
-        } else {
-          hs = F.base + hr;
-          halo_grad<ND, BS, FINER, NV, NS>(sP, F, side, hr, d, hd, p2, ghal);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) phal[v] = sP[v * NS + hs];
-          Dhal = sD[hs]; hh = F.hn;
-        }
-        if (side) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { po[v] = pown[v]; g0[v] = gown[v]; pn[v] = phal[v]; g1[v] = ghal[v]; }
-          Do = Down; Dn = Dhal; ho = hd; hn = hh;
-        } else {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { po[v] = phal[v]; g0[v] = ghal[v]; pn[v] = pown[v]; g1[v] = gown[v]; }
-          Do = Dhal; Dn = Down; ho = hh; hn = hd;
-        }
-        fslot = CPB + side * MAXL1 + k;
-      }
-      float pl[NV], pr[NV];
-      double F_[NV];
-      const bool fast = p2 && ho == hn;
-      muscl_face<NV>(po, pn, g0, g1, ho, hn, Do, Dn, true, false, pl, pr, fast);
-      if (FLUX == 0) {
-        hll_flux<ND>(fl, pl, pr, d, F_);
-      } else {
-        float Ff[NV];
-        rusanov_flux<ND>(fl, pl, pr, face_interp(Do, Dn, ho, hn), d, Ff);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) F_[v] = (double)Ff[v];
-      }
-      float ao = sqrtf(gr * clampT(po[1])), an = sqrtf(gr * clampT(pn[1]));
-      float ct = fabsf(face_interp_f(pick<ND>(po + 2, d), pick<ND>(pn + 2, d), ho, hn, fast)) + face_interp_f(ao, an, ho, hn, fast);
-#pragma unroll
-      for (int v = 0; v < NV; ++v) sF[v * NG + fslot] = F_[v];
-      sC[fslot] = ct;
-    }
-    __syncthreads();
-    // ---- (2) divergence: R -= (mean_high - mean_low) / h, cfl += (c_high + c_low) / h
-#pragma unroll
-    for (int q = 0; q < C::CPT; ++q) {
-      int l = tid + q * NT;
-      if (l >= CPB) break;
-      int ii[3];
-      split<ND, BS>(l, ii);
-      double mh[NV], ml[NV];
-      float ch, cl;
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        double* m = side ? mh : ml;
-        float& cm = side ? ch : cl;
-        bool inner = side ? ii[d] < BS - 1 : ii[d] > 0;
-        const FaceInfo& F = side ? FH : FL;
-        if (inner || !FINER || F.kind != 3) {
-          int fs = inner ? (side ? l : l - stride) : CPB + side * MAXL1 + (ND == 3 ? ii[T2(d)] : 0) * BS + ii[T1(d)];
-#pragma unroll
-          for (int v = 0; v < NV; ++v) m[v] = sF[v * NG + fs];
-          cm = sC[fs];
-        } else {
-          constexpr int CNT = ND == 3 ? 4 : 2;
-          const float w = 1.0f / (float)CNT;
-          int a1 = ii[T1(d)], a2 = ND == 3 ? ii[T2(d)] : 0;
-#pragma unroll
-          for (int qq = 0; qq < CNT; ++qq) {
-            int fs = CPB + side * MAXL1 + (ND == 3 ? (2 * a2 + (qq >> 1)) * F.n1 : 0) + 2 * a1 + (qq & 1);
-            if (FLUX == 0) {
-#pragma unroll
-              for (int v = 0; v < NV; ++v) m[v] = qq == 0 ? sF[v * NG + fs] * (double)w : m[v] + sF[v * NG + fs] * (double)w;
-            } else {
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                float t = (float)sF[v * NG + fs] * w;
-                m[v] = qq == 0 ? (double)t : (double)((float)m[v] + t);
-              }
-            }
-            cm = qq == 0 ? sC[fs] * w : cm + sC[fs] * w;
-          }
-        }
-      }
-      if (FLUX == 0) {  // Float64 differences rounded into the Float32 residual once per dimension (R .-= ...)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) res[q][v] = (float)((double)res[q][v] - (mh[v] - ml[v]) * inv_hd_d);
-      } else {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) res[q][v] = res[q][v] - ((float)mh[v] - (float)ml[v]) / hd;
-      }
-      cf[q] = cf[q] + (p2 ? (ch + cl) * inv_hd : (ch + cl) / hd);
-    }
-    __syncthreads();
-    stride *= BS;
-  }
-#pragma unroll
-  for (int q = 0; q < C::CPT; ++q) {
-    int l = tid + q * NT;
-    if (l >= CPB) break;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) R[(int64_t)v * N + cell0 + l] = res[q][v];
-    cfl[cell0 + l] = cf[q];
   }
 }
 
@@ -1102,7 +813,7 @@ int launch_hyb_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int 
                     float* R, float* cfl) {
   using C = HybCfg<ND, BS, FINER>;
   // blocks with a finer neighbour: few, heavy (1 CTA/SM either way) -- measured faster in one pass
-  if (FINER || getenv("IBX_HYB_ONEPASS") != nullptr)
+  if (FINER)
     return launch_hyb_mode<ND, BS, FINER, P2, FLUX, 0>(c, D, blocks, n, f, P, S, R, cfl, nullptr, nullptr);
   // two passes through a global scratch holding the fluxes of the general faces
   constexpr int64_t NSL = 4 * C::FACE + C::NX;
@@ -1180,6 +891,10 @@ k_reg_sensor(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ f
   }
 }
 
+__global__ void fill_ones(float* __restrict__ S, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) S[i] = 1.0f;
+}
+
 // Q -> P, elementwise (src/cfd.jl:137-151)
 template <int ND>
 __global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restrict__ P, int64_t n, int64_t i0, int64_t i1) {
@@ -1193,31 +908,19 @@ __global__ void k_prim(ibx_fluid f, const float* __restrict__ Q, float* __restri
   }
 }
 
+// JST sensor of the listed blocks through the general tile kernel (2-D meshes, block sizes 4 and 2, cross-check in 3-D)
 template <int ND, int BS, bool FINER>
-int launch_pair(ibx_ctx* c, const ibx_domain& D, const int32_t* sens_blocks, int n_sens, const int32_t* flux_blocks,
-                int n_flux, ibx_fluid f, int flux_kind, const float* P, float* S, float* R, float* cfl, int stage) {
+int launch_tile_sensor(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* P, float* S) {
   using C = Cfg<ND, BS, FINER>;
-  if (stage == 0) {
-    if (n_sens == 0) return IBX_OK;
-    int rc;
-    if (C::SMEM_SENSOR > 48 * 1024) {
-      if ((rc = ensure_dyn_smem(c, (const void*)k_tile_sensor<ND, BS, FINER, true>, C::SMEM_SENSOR))) return rc;
-      if ((rc = ensure_dyn_smem(c, (const void*)k_tile_sensor<ND, BS, FINER, false>, C::SMEM_SENSOR))) return rc;
-    }
-    if (D.all_pow2) k_tile_sensor<ND, BS, FINER, true><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
-    else k_tile_sensor<ND, BS, FINER, false><<<n_sens, C::NT, C::SMEM_SENSOR, c->stream>>>(sens_blocks, D.d_block_faces, D.d_block_h, P, S);
-    LAUNCH_CHECK();
-  } else {
-    if (n_flux == 0) return IBX_OK;
-    int rc;
-    if ((rc = ensure_dyn_smem(c, (const void*)k_tile_flux<ND, BS, FINER, 0>, C::SMEM_FLUX))) return rc;
-    if ((rc = ensure_dyn_smem(c, (const void*)k_tile_flux<ND, BS, FINER, 1>, C::SMEM_FLUX))) return rc;
-    if (flux_kind == 0)
-      k_tile_flux<ND, BS, FINER, 0><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
-    else
-      k_tile_flux<ND, BS, FINER, 1><<<n_flux, C::NT, C::SMEM_FLUX, c->stream>>>(flux_blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, R, cfl);
-    LAUNCH_CHECK();
+  if (n == 0) return IBX_OK;
+  int rc;
+  if (C::SMEM_SENSOR > 48 * 1024) {
+    if ((rc = ensure_dyn_smem(c, (const void*)k_tile_sensor<ND, BS, FINER, true>, C::SMEM_SENSOR))) return rc;
+    if ((rc = ensure_dyn_smem(c, (const void*)k_tile_sensor<ND, BS, FINER, false>, C::SMEM_SENSOR))) return rc;
   }
+  if (D.all_pow2) k_tile_sensor<ND, BS, FINER, true><<<n, C::NT, C::SMEM_SENSOR, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, P, S);
+  else k_tile_sensor<ND, BS, FINER, false><<<n, C::NT, C::SMEM_SENSOR, c->stream>>>(blocks, D.d_block_faces, D.d_block_h, P, S);
+  LAUNCH_CHECK();
   return IBX_OK;
 }
 
@@ -1250,36 +953,23 @@ int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
     }
     CU(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
   }
-  const bool side = getenv("IBX_ONE_STREAM") == nullptr;
-  cudaStream_t sp = side ? c->aux_stream[0] : c->stream, sf = side ? c->aux_stream[1] : c->stream;
-  if (side) {
-    CU(cudaEventRecord(c->aux_fork, c->stream));
-    CU(cudaStreamWaitEvent(sp, c->aux_fork, 0));
-    CU(cudaStreamWaitEvent(sf, c->aux_fork, 0));
-  }
-  // IBX_GEN_OLD=1: the general faces through the generic neighbour-list code of k_hyb_flux MODE 1 (cross-check of gen.cu)
-  const bool gen_old = getenv("IBX_GEN_OLD") != nullptr;
+  cudaStream_t sp = c->aux_stream[0], sf = c->aux_stream[1];
+  CU(cudaEventRecord(c->aux_fork, c->stream));
+  CU(cudaStreamWaitEvent(sp, c->aux_fork, 0));
+  CU(cudaStreamWaitEvent(sf, c->aux_fork, 0));
   if (D.n_own_plain) {
-    if (!gen_old) rc = general_faces(c, D, D.d_blk_own_plain, D.n_own_plain, false, f, flux_kind, P, S, GFp, GCp, sp);
-    else if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, false, true, 0, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
-    else rc = launch_hyb_mode<ND, BS, false, true, 1, 1>(c, D, D.d_blk_own_plain, D.n_own_plain, f, P, S, R, cfl, GFp, GCp, sp);
-    if (rc) return rc;
+    if ((rc = general_faces(c, D, D.d_blk_own_plain, D.n_own_plain, false, f, flux_kind, P, S, GFp, GCp, sp))) return rc;
     if ((rc = march_flux(c, D, D.d_blk_own_plain, D.n_own_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp, sp))) return rc;
   }
   if (D.n_own_finer) {
-    if (!gen_old) rc = general_faces(c, D, D.d_blk_own_finer, D.n_own_finer, true, f, flux_kind, P, S, GFf, GCf, sf);
-    else if (flux_kind == 0) rc = launch_hyb_mode<ND, BS, true, true, 0, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
-    else rc = launch_hyb_mode<ND, BS, true, true, 1, 1>(c, D, D.d_blk_own_finer, D.n_own_finer, f, P, S, R, cfl, GFf, GCf, sf);
-    if (rc) return rc;
+    if ((rc = general_faces(c, D, D.d_blk_own_finer, D.n_own_finer, true, f, flux_kind, P, S, GFf, GCf, sf))) return rc;
     if ((rc = march_flux(c, D, D.d_blk_own_finer, D.n_own_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf, sf))) return rc;
   }
   if ((rc = march_flux(c, D, D.d_blk_own_regular, D.n_own_regular, 0, f, flux_kind, P, S, R, cfl, nullptr, nullptr, c->stream))) return rc;
-  if (side) {
-    CU(cudaEventRecord(c->aux_join[0], sp));
-    CU(cudaEventRecord(c->aux_join[1], sf));
-    CU(cudaStreamWaitEvent(c->stream, c->aux_join[0], 0));
-    CU(cudaStreamWaitEvent(c->stream, c->aux_join[1], 0));
-  }
+  CU(cudaEventRecord(c->aux_join[0], sp));
+  CU(cudaEventRecord(c->aux_join[1], sf));
+  CU(cudaStreamWaitEvent(c->stream, c->aux_join[0], 0));
+  CU(cudaStreamWaitEvent(c->stream, c->aux_join[1], 0));
   return IBX_OK;
 }
 
@@ -1308,9 +998,16 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   }
   int rc = IBX_OK;
   // sensor on every local block (owned + halo blocks of a shard), fluxes on the owned blocks only
-  bool direct = false;
-  if constexpr (ND == 3 && BS == 8) direct = getenv("IBX_SENSOR_TILES") == nullptr;   // IBX_SENSOR_TILES=1: the tile kernels (cross-check)
-  if (direct) {
+  // option "path" = 1 (ibx_set_option): tile kernels for the sensor and the fluxes also where the marching kernels
+  // apply -- an independent implementation kept as the fallback (2-D, block sizes 4 / 2, non-power-of-two spacings)
+  // and as the cross-check of the marching path (same bits)
+  const bool march = ND == 3 && BS == 8 && march_supported(D) && c->opt_path == 0;
+  const bool direct = ND == 3 && BS == 8 && c->opt_path == 0;
+  if (c->opt_sensor == 0) {
+    // MUSCL(...; D = nothing) (src/ImmersedBoundary.jl:1141): the blend with D == 1 returns uL, uR unchanged
+    fill_ones<<<grid_for(N, 256, c->sm_count, 16), 256, 0, c->stream>>>(S, N);
+    LAUNCH_CHECK();
+  } else if (direct) {
     if ((rc = sensor_regular(c, D, D.d_blk_all_regular, D.n_all_regular, P, S))) return rc;
   } else if (D.n_all_regular) {
     using RC = RegCfg<ND, BS>;
@@ -1320,25 +1017,25 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   }
   // irregular blocks: straight from global memory (gen.cu; 0.10 ms instead of 0.25 ms on C4 -- for regular blocks the
   // lean tile kernel above stays ahead, 0.22 vs 0.38 ms: boundary cells make up 58 % of a block)
-  if (direct) {
+  if (c->opt_sensor == 0) {
+  } else if (direct) {
     if ((rc = sensor_direct(c, D, D.d_blk_all_plain, D.n_all_plain, P, S))) return rc;
     if ((rc = sensor_direct(c, D, D.d_blk_all_finer, D.n_all_finer, P, S))) return rc;
   } else {
-    if ((rc = launch_pair<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
-    if ((rc = launch_pair<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, nullptr, 0, f, flux_kind, P, S, R, cfl, 0))) return rc;
+    if ((rc = launch_tile_sensor<ND, BS, false>(c, D, D.d_blk_all_plain, D.n_all_plain, P, S))) return rc;
+    if ((rc = launch_tile_sensor<ND, BS, true>(c, D, D.d_blk_all_finer, D.n_all_finer, P, S))) return rc;
   }
   // 3-D 8^3 blocks with power-of-two spacings: pencil-marching kernel (march.cu) on every owned block; the general
   // faces of the irregular blocks are computed first (MODE 1) and handed over through a global scratch
   if constexpr (ND == 3 && BS == 8) {
-    if (march_supported(D) && getenv("IBX_NO_MARCH") == nullptr) return run_march<ND, BS>(c, D, f, flux_kind, P, S, R, cfl);
+    if (march) return run_march<ND, BS>(c, D, f, flux_kind, P, S, R, cfl);
   }
+  if (c->opt_arith != 0)
+    return fail(IBX_ERR_UNSUPPORTED, "ibx_residual_euler: arithmetic = 1 (fast) exists for the marching kernels only (3-D, block size 8, "
+                                     "power-of-two spacings, path = 0)");
   // fluxes: regular blocks (all neighbours same level) through the lean kernel, the rest through the general one
   if ((rc = D.all_pow2 ? launch_reg<ND, BS, true>(c, D, f, flux_kind, P, S, R, cfl) : launch_reg<ND, BS, false>(c, D, f, flux_kind, P, S, R, cfl))) return rc;
-  // IBX_TILE_GENERAL=1 routes the irregular blocks through the older general tile kernel (cross-check)
-  if (getenv("IBX_TILE_GENERAL") != nullptr) {
-    if ((rc = launch_pair<ND, BS, false>(c, D, nullptr, 0, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl, 1))) return rc;
-    if ((rc = launch_pair<ND, BS, true>(c, D, nullptr, 0, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl, 1))) return rc;
-  } else if (D.all_pow2) {
+  if (D.all_pow2) {
     if ((rc = launch_hyb<ND, BS, false, true>(c, D, D.d_blk_own_plain, D.n_own_plain, f, flux_kind, P, S, R, cfl))) return rc;
     if ((rc = launch_hyb<ND, BS, true, true>(c, D, D.d_blk_own_finer, D.n_own_finer, f, flux_kind, P, S, R, cfl))) return rc;
   } else {

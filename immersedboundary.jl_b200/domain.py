@@ -42,6 +42,36 @@ def launch_count():
     return n.value
 
 
+def set_option(name, value):
+    """``ibx_set_option``: run-time options of the fused Euler residual -- ``"arithmetic"`` (0 reference-exact, 1 fast),
+    ``"path"`` (0 marching kernels, 1 tile kernels, 2 gather kernels), ``"sensor"`` (1 JST blend, 0 ``D = nothing``)."""
+    call("ibx_set_option", context(), name.encode(), int(value))
+
+
+def get_option(name):
+    v = C.c_int()
+    call("ibx_get_option", context(), name.encode(), C.byref(v))
+    return v.value
+
+
+class options:
+    """``with ib.options(path=1): ...`` -- set options for a block and restore them afterwards."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = get_option(k)
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
+
+
 # --------------------------------------------------------------------------------- device arrays
 class DeviceArray:
     """Opaque float32 device array (rows x cols, column-major): what ``conv_to_backend`` would produce.

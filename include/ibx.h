@@ -320,6 +320,18 @@ int ibx_block_pinv(ibx_ctx* c, ibx_array D, int nv, ibx_array Dinv);
 int ibx_block_apply(ibx_ctx* c, ibx_array Dinv, int nv, ibx_array v, ibx_array out);
 
 /* ------------------------------------------------------------------ fused, block-structured residuals */
+/* Run-time options of the fused Euler residual, per context (they replace the IBX_* environment switches of round 1).
+ *   "arithmetic": 0 (default) reference-exact -- no FMA contraction, Float64 HLL combination and Green-Gauss sums like
+ *                   src/cfd.jl:504-507 / src/ImmersedBoundary.jl:918-926: bit-identical to the oracle;
+ *                 1 fast -- Float32 flux, FMA contraction, approximate reciprocals: within the north-star tolerance when the
+ *                   error is scaled by the face fluxes, not bit-identical.
+ *   "path":       0 (default) marching kernels where they apply (3-D, block size 8, power-of-two spacings), tile kernels
+ *                   elsewhere; 1 tile kernels everywhere; 2 per-cell gather kernels.  1 and 2 are independent
+ *                   implementations kept as fallbacks and cross-checks (same bits as 0).
+ *   "sensor":     1 (default) MUSCL(...; D = JST_sensor(p)); 0 MUSCL(...; D = nothing)
+ *                   (src/ImmersedBoundary.jl:1117,1141): plain limited reconstruction. */
+int ibx_set_option(ibx_ctx* c, const char* name, int value);
+int ibx_get_option(ibx_ctx* c, const char* name, int* value);
 /* Linear advection residual of test/advection.jl:67-83 on the whole domain:
  * ud = -sum_dim GG(upwind MUSCL flux), spec = max_dim UGG(at_faces(C_dim)). u, ud, spec: N; C: N x nd. */
 int ibx_residual_advection(ibx_ctx* c, const ibx_domain* d, ibx_array u, ibx_array C, ibx_array ud, ibx_array spec);

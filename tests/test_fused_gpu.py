@@ -140,23 +140,18 @@ def test_end_to_end_host_call_and_properties(get_case, ib):
 
 @pytest.mark.parametrize("name,mps", [("rae2822", 10_000), ("sphere3d", 40_000)])
 def test_tile_kernels_match_gather_kernels(get_case, ib, name, mps):
-    """Two independent device implementations of the same residual: the shared-memory tile kernels (default) and
-    the per-cell gather kernels (IBX_GENERIC=1, also the fallback for odd block sizes)."""
-    import os
+    """Two independent device implementations of the same residual: the shared-memory tile / marching kernels (default) and
+    the per-cell gather kernels (option path = 2, also the fallback for odd block sizes)."""
     c = get_case(name, mps, upload=True)
     fl = ib.Fluid()
     N, nd = len(c.dom), c.dom.ndims
     Q = ib.DeviceArray.from_host(ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.dom.cells()[0])))
     out = []
-    for generic in (False, True):
-        if generic:
-            os.environ["IBX_GENERIC"] = "1"
-        try:
+    for path in (0, 2):
+        with ib.options(path=path):
             R, cf = ib.DeviceArray(N, nd + 2, False), ib.DeviceArray(N, 1, True)
             ib.residual_euler(c.dom, fl, Q, R, cf)
             out.append((R.to_host(), cf.to_host()))
-        finally:
-            os.environ.pop("IBX_GENERIC", None)
     rel, scaled = _rel_err(out[0][0], out[1][0])
     assert scaled < 1e-6 and rel < 1e-5, (rel, scaled)
     assert np.allclose(out[0][1], out[1][1], rtol=1e-6)
@@ -164,10 +159,10 @@ def test_tile_kernels_match_gather_kernels(get_case, ib, name, mps):
 
 @pytest.mark.parametrize("flux", ["hll", "sensor"])
 def test_marching_kernels_bit_identical_to_tile_kernels_and_oracle(get_case, ib, oracle, flux):
-    """3-D 8^3 blocks run the pencil-marching kernel (march.cu), the dedicated general-face kernel and the direct /
-    batched sensor kernels (gen.cu).  Each has an independent predecessor selectable by an environment switch; all
-    variants must give the SAME BITS, and those bits must be the oracle's (integer-exact claim: no tolerance)."""
-    import os
+    """3-D 8^3 blocks run the pencil-marching kernel (march_kernel.cuh), the dedicated general-face kernel and the direct /
+    batched sensor kernels (gen.cu).  Two independent implementations stay selectable (ibx_set_option "path": 1 = tile
+    kernels for sensor and fluxes, 2 = per-cell gather kernels); all three must give the SAME BITS, and those bits must
+    be the oracle's (integer-exact claim: no tolerance)."""
     c = get_case("sphere3d", 40_000, upload=True)
     E, cfd = oracle.euler, oracle.cfd
     fl, ofl = ib.Fluid(), cfd.Fluid()
@@ -178,19 +173,11 @@ def test_marching_kernels_bit_identical_to_tile_kernels_and_oracle(get_case, ib,
     Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
     Q = ib.DeviceArray.from_host(Q0)
     res = {}
-    for label, env in (("default", {}), ("tile", {"IBX_NO_MARCH": "1"}), ("generic_faces", {"IBX_GEN_OLD": "1"}),
-                       ("tile_sensors", {"IBX_SENSOR_TILES": "1"}), ("one_thread_per_pencil", {"IBX_MARCH_SEG": "1"}),
-                       ("scalar_fp32", {"IBX_MARCH_SCALAR": "1"}), ("middle_face_twice", {"IBX_MARCH_NOSHARE": "1"}),
-                       ("hll_on_lr_pairs", {"IBX_MARCH_HLR": "1"}),
-                       ("one_stream", {"IBX_ONE_STREAM": "1"})):
-        os.environ.update(env)
-        try:
+    for label, path in (("default", 0), ("tile", 1), ("gather", 2)):
+        with ib.options(path=path):
             R, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True)
             ib.residual_euler(c.dom, fl, Q, R, cf, flux=flux)
             res[label] = (R.to_host(), cf.to_host())
-        finally:
-            for k in env:
-                os.environ.pop(k, None)
     for label, (R, cf) in res.items():
         assert np.array_equal(R, res["default"][0]) and np.array_equal(cf, res["default"][1]), label
     Ro, co = np.zeros_like(Q0), np.zeros(N, F32)
@@ -238,3 +225,60 @@ def test_coarse_multigrid_levels_use_tiles(get_case, ib, oracle):
         rel, scaled = _rel_err(R.to_host(), Ro)
         assert scaled < 2e-6 and rel < 1e-5, (dom.mesh.block_size, rel, scaled)
         assert np.allclose(cf.to_host(), co, rtol=1e-5)
+
+
+def test_fast_arithmetic_is_within_the_flux_scaled_tolerance(get_case, ib, oracle):
+    """Option arithmetic = 1 (Float32 flux, FMA contraction, approximate reciprocals): NOT bit-identical, but within the
+    north-star 1e-5 per cell when the error is scaled by the face fluxes as SURVEY.md section 7 defines it; under the
+    stricter residual-scale normalisation of this file it is not (both numbers are printed by bench.py)."""
+    from bench import flux_scaled_error
+    c = get_case("sphere3d", 40_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    N = len(c.dom)
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
+    Q = ib.DeviceArray.from_host(Q0)
+    Ro, co = np.zeros_like(Q0), np.zeros(N, F32)
+    c.odom(E.euler_residual(ofl), Q0.copy(), Ro, co)
+    with ib.options(arithmetic=1):
+        R, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True)
+        ib.residual_euler(c.dom, fl, Q, R, cf)
+        Rf, cff = R.to_host(), cf.to_host()
+    assert ib.get_option("arithmetic") == 0
+    err = flux_scaled_error(c.dom.cells()[1], Q0, Rf, Ro)
+    assert err.max() < 1e-5, err.max()
+    assert not np.array_equal(Rf, Ro)                     # it really is a different arithmetic
+    assert np.allclose(cff, co, rtol=1e-6)
+    with pytest.raises(ib.IbxError):
+        with ib.options(arithmetic=1, path=1):
+            ib.residual_euler(c.dom, fl, Q, R, cf)          # fast arithmetic exists for the marching kernels only
+
+
+@pytest.mark.parametrize("name,mps", [("rae2822", 10_000), ("sphere3d", 40_000)])
+def test_residual_without_sensor_blend(get_case, ib, oracle, name, mps):
+    """Option sensor = 0: MUSCL(...; D = nothing) (src/ImmersedBoundary.jl:1117,1141) -- plain limited reconstruction,
+    bit-identical to the oracle composition with D=None."""
+    from oracle.domain import JST_sensor, MUSCL, at_faces, cell_gradient, green_gauss, unsigned_green_gauss
+    c = get_case(name, mps, upload=True)
+    cfd = oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    N, nd = len(c.dom), c.dom.ndims
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.odom.centers))
+
+    def f(part, Q, R, cfl):
+        P = cfd.state2primitive(ofl, Q)
+        a = cfd.speed_of_sound(ofl, P[:, 1])
+        R[...] = 0
+        cfl[...] = 0
+        for dim in range(part.ndims):
+            gP = cell_gradient(part, P, dim)
+            PL, PR = MUSCL(part, P, gP, dim)
+            R[...] = R - green_gauss(part, cfd.inviscid_fluxes_hll(ofl, PL, PR, dim), dim)
+            cfl += unsigned_green_gauss(part, np.abs(at_faces(part, P[:, 2 + dim], dim)) + at_faces(part, a, dim), dim)
+
+    Ro, co = np.zeros_like(Q0), np.zeros(N, F32)
+    c.odom(f, Q0.copy(), Ro, co)
+    with ib.options(sensor=0):
+        R, cf = ib.DeviceArray(N, nd + 2, False), ib.DeviceArray(N, 1, True)
+        ib.residual_euler(c.dom, fl, ib.DeviceArray.from_host(Q0), R, cf)
+    assert np.array_equal(R.to_host(), Ro) and np.array_equal(cf.to_host(), co)

@@ -13,7 +13,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 F32 = np.float32
-MACH, ALPHA, CFL, STEPS = 0.73, 2.31, F32(0.4), 10
+MACH, ALPHA, CFL, STEPS = 0.73, 2.31, F32(0.4), 20
 
 
 def _coefficients(Fxy):
