@@ -311,6 +311,37 @@ __global__ void k_accumulate(const float* __restrict__ v, int64_t vrows, const i
   }
 }
 
+// the same with the `f` and `op` keyword arguments of src/accumulator.jl:78-111: f applied to the gathered values (after the
+// Delta subtraction, before the weights), rows reduced with op in list order.  F: 0 identity, 1 abs, 2 square, 3 sign.
+// OP: 0 +, 1 max, 2 min, 3 *.  An empty row keeps the zero of `vnew .= 0`.
+template <int F, int OP>
+__global__ void k_accumulate_ex(const float* __restrict__ v, int64_t vrows, const int32_t* __restrict__ ptr,
+                                const int32_t* __restrict__ idx, const float* __restrict__ w, float* __restrict__ out,
+                                int64_t n, int cols, int delta) {
+  int64_t tot = n * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = t % n, col = t / n;
+    const float* vc = v + col * vrows;
+    int32_t b = ptr[row], e = ptr[row + 1];
+    float acc = 0.0f;
+    float self = (delta && w) ? vc[row] : 0.0f;
+    for (int32_t k = b; k < e; ++k) {
+      float val = vc[idx[k]];
+      if (w && delta) val = val - self;
+      if (F == 1) val = fabsf(val);
+      if (F == 2) val = val * val;
+      if (F == 3) val = (float)((val > 0.0f) - (val < 0.0f));
+      if (w) val = val * w[k];
+      if (k == b) acc = val;
+      else if (OP == 0) acc = acc + val;
+      else if (OP == 1) acc = fmaxf(acc, val);
+      else if (OP == 2) acc = fminf(acc, val);
+      else acc = acc * val;
+    }
+    out[t] = acc;
+  }
+}
+
 // a[ghost, col] = eta * ia + (1 - eta) * ba   (src/ImmersedBoundary.jl:1242-1245); ba array or scalar
 __global__ void k_bc_blend(float* __restrict__ a, int64_t arows, const int32_t* __restrict__ ghost,
                            const float* __restrict__ eta, const float* __restrict__ ia, const float* __restrict__ ba,
@@ -730,6 +761,28 @@ int ibx_accumulate(ibx_ctx* c, const ibx_accum* a, ibx_array v, int delta, ibx_a
   SHAPE(O.rows == A->n_out && O.cols == V.cols, "out must be n_output x nv");
   if (delta) SHAPE(V.rows >= A->n_out, "delta form needs v[row] for every output row");
   return accumulate_raw(c, A->d_ptr, A->d_idx, A->weighted ? A->d_w : nullptr, A->n_out, V, O, delta);
+}
+
+int ibx_accumulate_ex(ibx_ctx* c, const ibx_accum* a, ibx_array v, int delta, int f_kind, int op_kind, ibx_array out) {
+  CHECK_CTX(c);
+  ibx_accum* A = find_accum(a);
+  if (!A) return fail(IBX_ERR_ARG, "ibx_accumulate_ex: unknown accumulator handle");
+  if (!A->uploaded) return fail(IBX_ERR_STATE, "ibx_accumulate_ex: accumulator not uploaded (ibx_accum_upload)");
+  if (f_kind < 0 || f_kind > 3 || op_kind < 0 || op_kind > 3)
+    return fail(IBX_ERR_ARG, "ibx_accumulate_ex: f_kind in 0..3 (identity, abs, square, sign), op_kind in 0..3 (+, max, min, *)");
+  if (f_kind == 0 && op_kind == 0) return ibx_accumulate(c, a, v, delta, out);
+  GET_ARR(V, v);
+  GET_ARR(O, out);
+  SHAPE(O.rows == A->n_out && O.cols == V.cols, "out must be n_output x nv");
+  if (delta) SHAPE(V.rows >= A->n_out, "delta form needs v[row] for every output row");
+  const float* w = A->weighted ? A->d_w : nullptr;
+#define GO(F, OP) k_accumulate_ex<F, OP><<<GRID(A->n_out * V.cols)>>>(V.p, V.rows, A->d_ptr, A->d_idx, w, O.p, A->n_out, (int)V.cols, delta)
+#define ROW(F) switch (op_kind) { case 0: GO(F, 0); break; case 1: GO(F, 1); break; case 2: GO(F, 2); break; default: GO(F, 3); }
+  switch (f_kind) { case 0: ROW(0) break; case 1: ROW(1) break; case 2: ROW(2) break; default: ROW(3) }
+#undef ROW
+#undef GO
+  LAUNCH_CHECK();
+  return IBX_OK;
 }
 
 #define BDRY(B, D, b, part)                                                                                    \

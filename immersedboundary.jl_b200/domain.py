@@ -249,15 +249,22 @@ class Accumulator:
         call("ibx_accum_tables", self._h, ptr(p), ptr(i), ptr(w))
         return p, i, w
 
-    def __call__(self, v, delta=False):
-        """``acc(v; Δ)`` (``src/accumulator.jl:78-130``); v: DeviceArray or host array."""
+    _F = {None: 0, "identity": 0, "abs": 1, "abs2": 2, "square": 2, "sign": 3}
+    _OP = {None: 0, "+": 0, "sum": 0, "max": 1, "min": 2, "*": 3, "prod": 3}
+
+    def __call__(self, v, delta=False, f=None, op=None):
+        """``acc(v; Δ, f, op)`` (``src/accumulator.jl:78-130``); v: DeviceArray or host array.  ``f`` / ``op`` by name
+        (``"abs"``, ``"abs2"``, ``"sign"``; ``"+"``, ``"max"``, ``"min"``, ``"*"``): closures do not cross the C ABI."""
         host = not isinstance(v, DeviceArray)
         dv = DeviceArray.from_host(v) if host else v
         if not self._uploaded:
             call("ibx_accum_upload", context(), self._h)
             self._uploaded = True
         out = DeviceArray(self.n_output, dv.cols, dv.vector)
-        call("ibx_accumulate", context(), self._h, dv.h, int(delta), out.h)
+        if f is None and op is None:
+            call("ibx_accumulate", context(), self._h, dv.h, int(delta), out.h)
+        else:
+            call("ibx_accumulate_ex", context(), self._h, dv.h, int(delta), self._F[f], self._OP[op], out.h)
         return out.to_host() if host else out
 
 

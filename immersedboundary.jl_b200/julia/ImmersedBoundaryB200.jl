@@ -472,10 +472,29 @@ function Accumulator(h::Ptr{Cvoid})
     acc = Accumulator(h, n[], false)
     finalizer(a -> ccall((:ibx_accum_free, libibx), Cint, (Ptr{Cvoid},), a.h), acc)
 end
-function (acc::Accumulator)(v::IBXArray; Δ::Bool = false)
+# `f` / `op` of src/accumulator.jl:78-81: a closure cannot cross the C ABI, so the functions the package itself passes are
+# mapped to codes (ibx_accumulate_ex); any other f must be elementwise and Δ = false (then f(v[stencil]) == f.(v)[stencil]).
+const _ACC_F = IdDict{Any, Cint}(identity => 0, abs => 1, abs2 => 2, sign => 3)
+const _ACC_OP = IdDict{Any, Cint}((+) => 0, max => 1, min => 2, (*) => 3)
+function (acc::Accumulator)(v::IBXArray; Δ::Bool = false, f = identity, op = +)
     acc.uploaded || (check(ccall((:ibx_accum_upload, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), context(), acc.h)); acc.uploaded = true)
     out = length(v.dims) == 1 ? IBXArray{1}((acc.n_output,)) : IBXArray{2}((acc.n_output, ncols(v)))
-    check(ccall((:ibx_accumulate, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Int64), context(), acc.h, v.h, Δ, out.h)); out
+    haskey(_ACC_OP, op) || error("Accumulator: op must be one of +, max, min, * on the B200 backend")
+    if !haskey(_ACC_F, f)
+        Δ && error("Accumulator: an arbitrary f with Δ = true cannot be evaluated on the device (use abs, abs2 or sign)")
+        v = f(v); f = identity          # elementwise f applied on the device array first
+    end
+    check(ccall((:ibx_accumulate_ex, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint, Cint, Int64),
+                context(), acc.h, v.h, Δ, _ACC_F[f], _ACC_OP[op], out.h)); out
+end
+
+"""Run-time options of the fused Euler residual (`ibx_set_option`): `:arithmetic` (0 reference-exact, 1 fast),
+`:path` (0 marching kernels, 1 tile kernels, 2 gather kernels), `:sensor` (1 JST blend, 0 `D = nothing`)."""
+set_option(name::Union{Symbol, String}, value::Integer) =
+    check(ccall((:ibx_set_option, libibx), Cint, (Ptr{Cvoid}, Cstring, Cint), context(), String(name), value))
+function get_option(name::Union{Symbol, String})
+    v = Ref{Cint}(0)
+    check(ccall((:ibx_get_option, libibx), Cint, (Ptr{Cvoid}, Cstring, Ref{Cint}), context(), String(name), v)); Int(v[])
 end
 "`Interpolator(X, Xc; linear, k)` (src/nninterp.jl:85-138); X, Xc are (nd, npoints) like the reference and are passed row-major."
 function Interpolator(X::AbstractMatrix, Xc::AbstractMatrix; linear::Bool = true, k::Int = 0)

@@ -289,6 +289,12 @@ int ibx_wale(ibx_ctx* c, ibx_array Delta, const ibx_array* g, float Cw, ibx_arra
 /* ------------------------------------------------------------------ accumulators, IB ghost update (K8, K9) */
 /* out = acc(v)  (src/accumulator.jl:78-130); delta: subtract v[row] first (Delta = true) */
 int ibx_accumulate(ibx_ctx* c, const ibx_accum* a, ibx_array v, int delta, ibx_array out);
+/* the `f` and `op` keyword arguments of the same call (src/accumulator.jl:78-81): f is applied to the gathered values
+ * (after the Delta subtraction, before the weights), the stencil rows are reduced with op in list order.
+ * f_kind: 0 identity, 1 abs, 2 x -> x^2, 3 sign; op_kind: 0 +, 1 max, 2 min, 3 *.  (A closure cannot cross a C ABI: the
+ * Julia wrapper maps `abs`, `abs2`, `sign`, `+`, `max`, `min`, `*` to these codes and, for any other ELEMENTWISE f with
+ * Delta = false, applies f on the device array first -- f(v[stencil]) == f.(v)[stencil].) */
+int ibx_accumulate_ex(ibx_ctx* c, const ibx_accum* a, ibx_array v, int delta, int f_kind, int op_kind, ibx_array out);
 /* impose_bc! pieces (src/ImmersedBoundary.jl:1197-1247) for boundary b, chunk part */
 int ibx_bc_image_values(ibx_ctx* c, const ibx_domain* d, int b, int part, ibx_array a, ibx_array ia);   /* :1228 */
 int ibx_bc_normals(ibx_ctx* c, const ibx_domain* d, int b, int part, ibx_array out /* nghost x nd */);

@@ -43,3 +43,11 @@ out["sph_cfl_sum"] = np.float64(cf.astype(np.float64).sum())
 out["sph_ghosts_wall"] = d3.boundaries["wall"][1].ghost_indices.astype(np.int32)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_fixtures.npz"), **out)
 print({k: v.shape for k, v in out.items()})
+
+# ---- inputs for tools/gen_reference_fixtures.jl (the Julia pinning kit): the icosphere the 3-D STL tests use
+if "--icosphere" in sys.argv:
+    pts, tri = S.icosphere(1, 0.5)
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference")
+    os.makedirs(ref, exist_ok=True)
+    np.ascontiguousarray(pts, dtype=np.float32).tofile(os.path.join(ref, "icosphere1_points.f32"))           # npts x 3 C-order == 3 x npts Julia
+    np.ascontiguousarray(tri + 1, dtype=np.int64).tofile(os.path.join(ref, "icosphere1_triangles.i64"))     # 1-based

@@ -53,3 +53,17 @@ def test_gpu_reproduces_fixtures(ib):
     assert np.allclose(np.abs(Rg.astype(np.float64)).sum(axis=0), FIX["sph_R_abs"], rtol=1e-9, atol=0)
     assert np.allclose(Rg.astype(np.float64).sum(axis=0), FIX["sph_R_sum"], rtol=0, atol=1e-9 * FIX["sph_R_abs"].max())
     assert np.isclose(cg.astype(np.float64).sum(), FIX["sph_cfl_sum"], rtol=1e-10)
+
+
+def test_pinning_kit_file_format_round_trip(tmp_path):
+    """tools/gen_reference_fixtures.jl (for a Julia owner) and tests/test_reference_fixtures.py share a file format; with
+    no Julia here, exercise the consumer on files written FROM THE ORACLE in that format (a format test, not parity)."""
+    import subprocess
+    import sys
+    env = dict(os.environ, IBX_REFERENCE_FIXTURES=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fake_reference_fixtures.py"), str(tmp_path)],
+                       capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_reference_fixtures.py"), "-q", "-x"],
+                       capture_output=True, text=True, cwd=ROOT, env=env, timeout=600)
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:]

@@ -125,6 +125,16 @@ def test_accumulator_and_elementwise(ib, oracle):
                           oracle.accumulator.Accumulator(inds2, ws2)(v2, delta=True))
     un, oun = ib.Accumulator.from_lists(inds2), oracle.accumulator.Accumulator(inds2)
     assert np.array_equal(un(v2), oun(v2))
+    # the `f` and `op` keyword arguments (src/accumulator.jl:78-111), weighted with and without Delta, and unweighted
+    a2, oa2 = ib.Accumulator.from_lists(inds2, ws2), oracle.accumulator.Accumulator(inds2, ws2)
+    fs = {"abs": np.abs, "abs2": lambda x: x * x, "sign": np.sign}
+    ops = {"+": None, "max": np.maximum, "min": np.minimum, "*": lambda p, q: p * q}
+    for fname, f in fs.items():
+        for oname, op in ops.items():
+            for delta in (False, True):
+                assert np.array_equal(a2(v2, delta=delta, f=fname, op=oname), oa2(v2, delta=delta, f=f, op=op)), (fname, oname, delta)
+            assert np.array_equal(un(v2, f=fname, op=oname), oun(v2, f=f, op=op)), (fname, oname)
+    assert np.array_equal(acc(v, f="abs", op="max"), oacc(v, f=np.abs, op=np.maximum))     # empty rows stay 0
     kat = ib.Accumulator.from_lists([[0, 1], [1, 2, 3]], [[-1.0, 2.0], [3.0, 4.0, 5.0]])
     assert np.array_equal(kat(np.array([1, 2, 3, 4], F32)), np.array([3.0, 38.0], F32))  # src/accumulator.jl:25-34
     a, b = ib.DeviceArray.from_host(v), ib.DeviceArray.from_host(v[::-1].copy())
