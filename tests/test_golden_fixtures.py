@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 F32 = np.float32
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_fixtures.npz"))
 
 
