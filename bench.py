@@ -248,7 +248,11 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // world)))
+        # torchrun exports OMP_NUM_THREADS=1; the host-side builder is OpenMP code: give every rank its share of the cores
+        try:
+            C.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 8) // world))
+        except OSError:
+            pass
     ctx = ib.context(local_rank)
     t_setup = time.perf_counter()
     cells_target = args.cells if args.cells else CELLS_PER_GPU * world
@@ -332,6 +336,38 @@ def run_ours(args):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = n_global * args.steps / (ms_total * 1e-3)
+
+    # where a sharded step spends its time: each phase timed on its own (CUDA events, max over ranks), and the exchange volume
+    halo = None
+    if world > 1:
+        import torch
+        sc, rc_ = np.zeros(world, np.int64), np.zeros(world, np.int64)
+        ib._lib.call("ibx_halo_sizes", dom._h, world, ib._lib.ptr(sc), ib._lib.ptr(rc_))
+
+        def timed(fn, reps=20):
+            barrier()
+            ib._lib.call("ibx_timer_start", ctx)
+            for _ in range(reps):
+                fn()
+            ib._lib.call("ibx_timer_stop", ctx, C.byref(ms))
+            tt = torch.tensor([ms.value / reps], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        ms_x = timed(lambda: dom.halo_exchange(Q))
+        ms_g = timed(lambda: ib.ghost_update_euler(dom, fluid, Q, bcs))
+        ms_r = timed(lambda: ib.residual_euler(dom, fluid, Q, R, cfl))
+        vol = torch.tensor([float(sc.sum()), float(rc_.sum()), float((sc > 0).sum())], device="cuda")
+        vmax = vol.clone()
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+        halo = {"exchanges_per_step": 2, "collective": "grouped ncclSend/ncclRecv (pack kernel -> NCCL -> unpack kernel)",
+                "rows_sent_max_rank": int(vmax[0].item()), "rows_received_max_rank": int(vmax[1].item()),
+                "bytes_sent_per_exchange_max_rank": int(vmax[0].item()) * 20, "peers_max_rank": int(vmax[2].item()),
+                "ms_exchange_alone": ms_x, "ms_ghost_update_alone": ms_g, "ms_residual_alone": ms_r,
+                "ms_step": ms_step, "ms_exposed_communication": ms_step - ms_g - ms_r,
+                "coupled_families": sorted(dom.shard_info.get("coupled_families", ())),
+                "limiter": "latency of the two exchanges (3 dependent launches + NCCL each), not bandwidth: "
+                           f"{int(vmax[0].item()) * 20 / 1e6:.1f} MB per exchange"}
 
     # dominant kernel alone (CUDA events on the library's compute stream) for the roofline entry
     reps = max(3, min(args.steps, 10))
@@ -426,31 +462,57 @@ def run_ours(args):
                                       "api": "ibx_euler_step_host"}}
     else:
         # every rank: H2D of its shard's state (owned + halo rows) from pinned memory, the sharded step (halo exchange,
-        # ghost update, halo exchange, residual), D2H of its residual and CFL arrays; max over ranks
-        R_host, c_host = ib.pinned_empty((n_local, 5)), ib.pinned_empty((n_local,))
+        # ghost update, halo exchange, residual), D2H of its residual and CFL arrays; max over ranks.  Two independent
+        # evaluations in flight on alternating slots, like the single-GPU arm: the upload of one overlaps the compute and the
+        # download of the other (ibx_array_upload_async / _download_async / ibx_download_fence / _wait).
+        del R, cfl
+        Qd = [Q, ib.DeviceArray(n_local, 5, False)]
+        Rd = [ib.DeviceArray(n_local, 5, False) for _ in range(2)]
+        cd = [ib.DeviceArray(n_local, 1, True) for _ in range(2)]
+        Qh = [Q_host, ib.pinned_empty((n_local, 5))]
+        Qh[1][...] = Q_host
+        Rh = [ib.pinned_empty((n_local, 5)) for _ in range(2)]
+        ch = [ib.pinned_empty((n_local,)) for _ in range(2)]
 
-        def e2e_step():
-            Q.upload(Q_host)
-            step()
-            ib._lib.call("ibx_array_download", ctx, R.h, ib._lib.ptr(R_host))
-            ib._lib.call("ibx_array_download", ctx, cfl.h, ib._lib.ptr(c_host))
+        def begin(sl):
+            ib._lib.call("ibx_array_upload_async", ctx, Qd[sl].h, ib._lib.ptr(Qh[sl]))
+            dom.halo_exchange(Qd[sl])
+            ib.ghost_update_euler(dom, fluid, Qd[sl], bcs)
+            dom.halo_begin(Qd[sl])
+            ib.residual_euler(dom, fluid, Qd[sl], Rd[sl], cd[sl])
+            ib._lib.call("ibx_array_download_async", ctx, Rd[sl].h, ib._lib.ptr(Rh[sl]))
+            ib._lib.call("ibx_array_download_async", ctx, cd[sl].h, ib._lib.ptr(ch[sl]))
+            ib._lib.call("ibx_download_fence", ctx, sl)
 
-        e2e_step()
-        k = max(2, min(args.steps, 5))
+        def end(sl):
+            ib._lib.call("ibx_download_wait", ctx, sl)
+
+        for sl in range(2):
+            begin(sl)
+        for sl in range(2):
+            end(sl)
+        k = max(4, min(args.steps, 12))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(k):
-            e2e_step()
+        for i in range(k):
+            sl = i % 2
+            end(sl)
+            begin(sl)
+        for sl in range(2):
+            end(sl)
         barrier()
         import torch
         t = torch.tensor([time.perf_counter() - t0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        hb = torch.tensor([float(Q_host.nbytes), float(R_host.nbytes + c_host.nbytes)], device="cuda")
+        hb = torch.tensor([float(Q_host.nbytes), float(Rh[0].nbytes + ch[0].nbytes)], device="cuda")
         dist.all_reduce(hb)
         e2e = {"value": n_global * k / dt, "unit": "cell-updates/s", "h2d_bytes_per_step": int(hb[0].item()),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": dt / k * 1e3, "steps": k,
-               "api": "ibx_array_upload + sharded step + ibx_array_download on every rank (C ABI, pinned host buffers)"}
+               "host_gbs_aggregate": (hb[0].item() + hb[1].item()) * k / dt / 1e9,
+               "api": "ibx_array_upload_async + sharded step + ibx_array_download_async on every rank, two slots in flight "
+                      "(C ABI, pinned host buffers)"}
+        R, cfl = Rd[0], cd[0]
 
     if world > 1:
         ib._lib.call("ibx_comm_finalize", ctx)
@@ -472,7 +534,7 @@ def run_ours(args):
                    "cells": n_global, "cells_per_gpu": n_owned, "ghost_cells_rank0": n_ghost, "blocks": msh.nblocks,
                    "refinement_ball_radius": radius, "finest_level": args.level, "block_size": 8, "nv": 5, "partition": "contiguous block ranges, one per GPU",
                    "l2": "working set >> 126 MB L2, no flush needed", "setup_s": round(setup_s, 1)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "halo": halo,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": "ibx_residual_euler (k_prim + sensor kernels + general-face pass + k_march_flux)",

@@ -189,12 +189,22 @@ int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
     }
   }
   NC(g_nccl.GroupStart());
-  for (int peer = 0; peer < S.nranks; ++peer) {
-    int64_t ns = (int64_t)S.send_local[peer].size(), nr = (int64_t)S.recv_local[peer].size();
-    if (ns) NC(g_nccl.Send(S.d_sendbuf[peer], (size_t)ns * cols, NCCL_FLOAT32, peer, c->nccl_comm, c->comm_stream));
-    if (nr) NC(g_nccl.Recv(S.d_recvbuf[peer], (size_t)nr * cols, NCCL_FLOAT32, peer, c->nccl_comm, c->comm_stream));
+  {
+    // an error between GroupStart and GroupEnd must not leave the group open (the next NCCL call would hang): close it,
+    // poison the context, then report
+    int bad = 0;
+    for (int peer = 0; peer < S.nranks && !bad; ++peer) {
+      int64_t ns = (int64_t)S.send_local[peer].size(), nr = (int64_t)S.recv_local[peer].size();
+      if (ns) bad = g_nccl.Send(S.d_sendbuf[peer], (size_t)ns * cols, NCCL_FLOAT32, peer, c->nccl_comm, c->comm_stream);
+      if (nr && !bad) bad = g_nccl.Recv(S.d_recvbuf[peer], (size_t)nr * cols, NCCL_FLOAT32, peer, c->nccl_comm, c->comm_stream);
+    }
+    int end = g_nccl.GroupEnd();
+    if (bad || end) {
+      c->poisoned = true;
+      return fail(IBX_ERR_NCCL, std::string("NCCL error in the grouped halo send/recv: ") +
+                                    (g_nccl.GetErrorString ? g_nccl.GetErrorString(bad ? bad : end) : "unknown"));
+    }
   }
-  NC(g_nccl.GroupEnd());
   for (int peer = 0; peer < S.nranks; ++peer) {
     int64_t nr = (int64_t)S.recv_local[peer].size();
     if (nr && S.nranks > MAXPEER) {

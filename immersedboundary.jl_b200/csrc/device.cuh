@@ -41,6 +41,9 @@ struct ibx_ctx {
     bool busy = false;
   } e2e[2];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  // asynchronous array copies (ibx_array_upload_async / _download_async): [0] upload done, [1] compute done, [2 + slot] fences
+  cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool copy_fence_set[2] = {false, false};
   // side streams of the fused residual: the irregular-block passes run beside the regular-block kernel
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   cudaEvent_t aux_fork = nullptr, aux_join[2] = {nullptr, nullptr};

@@ -416,8 +416,9 @@ __global__ void k_clamped_update(float* __restrict__ Q, const float* __restrict_
 // ------------------------------------------------------------------ reductions: warp shuffle -> block -> one slot per block
 __device__ __forceinline__ double red_combine(int op, double a, double b) {
   switch (op) {
-    case 1: case 3: return fmax(a, b);
-    case 2: return fmin(a, b);
+    // Julia's maximum / minimum propagate NaN (fmax / fmin would drop it and hide a diverged field from the solver loops)
+    case 1: case 3: return (a != a || b != b) ? (double)NAN : fmax(a, b);
+    case 2: return (a != a || b != b) ? (double)NAN : fmin(a, b);
     default: return a + b;
   }
 }
@@ -486,7 +487,8 @@ static int reduce_impl(ibx_ctx* c, int op, const float* a, const float* b, const
     double acc = rop == 1 || rop == 3 ? (rop == 1 ? -INFINITY : 0.0) : (rop == 2 ? INFINITY : 0.0);
     for (int k = 0; k < gx; ++k) {
       double v = c->h_red[(size_t)col * gx + k];
-      acc = (rop == 1 || rop == 3) ? std::max(acc, v) : (rop == 2 ? std::min(acc, v) : acc + v);
+      if (rop != 0 && (v != v || acc != acc)) acc = NAN;   // NaN propagates through max / min like Julia's maximum / minimum
+      else acc = (rop == 1 || rop == 3) ? std::max(acc, v) : (rop == 2 ? std::min(acc, v) : acc + v);
     }
     out_per_col[col] = acc;
   }

@@ -84,15 +84,23 @@ int ibx_init(int device, ibx_ctx** out) {
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
   c->total_mem = prop.totalGlobalMem;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&c->ev0));
-  CU(cudaEventCreate(&c->ev1));
-  CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
   c->red_cap = 4096;
-  CU(cudaMalloc((void**)&c->d_red, c->red_cap * sizeof(double)));
-  CU(cudaMallocHost((void**)&c->h_red, c->red_cap * sizeof(double)));
+  // a failure below must not leak the half-built context: ibx_finalize releases whatever exists
+  auto setup = [&]() -> int {
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+    CU(cudaMalloc((void**)&c->d_red, c->red_cap * sizeof(double)));
+    CU(cudaMallocHost((void**)&c->h_red, c->red_cap * sizeof(double)));
+    return IBX_OK;
+  };
+  if (int rc = setup()) {
+    ibx_finalize(c);
+    return rc;
+  }
   *out = c;
   return IBX_OK;
 }
@@ -124,6 +132,8 @@ int ibx_finalize(ibx_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  for (auto& e : c->copy_ev)
+    if (e) cudaEventDestroy(e);
   delete c;
   return IBX_OK;
 }
@@ -257,6 +267,58 @@ int ibx_array_download(ibx_ctx* c, ibx_array a, float* host) {
   GET_ARR(A, a);
   CU(cudaMemcpyAsync(host, A.p, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  return IBX_OK;
+}
+
+static int ensure_copy_streams(ibx_ctx* c) {
+  if (!c->h2d_stream) {
+    CU(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  }
+  for (auto& e : c->copy_ev)
+    if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return IBX_OK;
+}
+
+int ibx_array_upload_async(ibx_ctx* c, ibx_array a, const float* host) {
+  CHECK_CTX(c);
+  GET_ARR(A, a);
+  int rc;
+  if ((rc = ensure_copy_streams(c))) return rc;
+  CU(cudaMemcpyAsync(A.p, host, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+  CU(cudaEventRecord(c->copy_ev[0], c->h2d_stream));
+  CU(cudaStreamWaitEvent(c->stream, c->copy_ev[0], 0));
+  CU(cudaStreamWaitEvent(c->comm_stream, c->copy_ev[0], 0));
+  return IBX_OK;
+}
+
+int ibx_array_download_async(ibx_ctx* c, ibx_array a, float* host) {
+  CHECK_CTX(c);
+  GET_ARR(A, a);
+  int rc;
+  if ((rc = ensure_copy_streams(c))) return rc;
+  CU(cudaEventRecord(c->copy_ev[1], c->stream));
+  CU(cudaStreamWaitEvent(c->d2h_stream, c->copy_ev[1], 0));
+  CU(cudaMemcpyAsync(host, A.p, (size_t)A.rows * A.cols * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+  return IBX_OK;
+}
+
+int ibx_download_fence(ibx_ctx* c, int slot) {
+  CHECK_CTX(c);
+  if (slot < 0 || slot > 1) return fail(IBX_ERR_ARG, "ibx_download_fence: slot must be 0 or 1");
+  int rc;
+  if ((rc = ensure_copy_streams(c))) return rc;
+  CU(cudaEventRecord(c->copy_ev[2 + slot], c->d2h_stream));
+  c->copy_fence_set[slot] = true;
+  return IBX_OK;
+}
+
+int ibx_download_wait(ibx_ctx* c, int slot) {
+  CHECK_CTX(c);
+  if (slot < 0 || slot > 1) return fail(IBX_ERR_ARG, "ibx_download_wait: slot must be 0 or 1");
+  if (!c->copy_fence_set[slot]) return IBX_OK;
+  CU(cudaEventSynchronize(c->copy_ev[2 + slot]));
+  c->copy_fence_set[slot] = false;
   return IBX_OK;
 }
 

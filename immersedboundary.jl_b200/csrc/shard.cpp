@@ -76,6 +76,7 @@ int ibx_domain_shard(const ibx_domain* gh, int rank, int nranks, ibx_domain** ou
   const ibx_domain& G = *Gp;
   IBX_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "rank out of range");
   IBX_REQUIRE(G.two_to_one, "sharding needs a mesh whose block contacts are same-level or 2:1");
+  IBX_REQUIRE(G.ncells < (int64_t)2147483647, "more than 2^31-1 cells: the Int32 request / send lists would wrap");
   int nd = G.nd, bs = G.block_size;
   int64_t cpb = 1;
   for (int d = 0; d < nd; ++d) cpb *= bs;

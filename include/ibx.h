@@ -200,6 +200,16 @@ int ibx_array_free(ibx_ctx* c, ibx_array a);
 int ibx_array_shape(ibx_ctx* c, ibx_array a, int64_t* rows, int64_t* cols);
 int ibx_array_upload(ibx_ctx* c, ibx_array a, const float* host);        /* column-major rows x cols */
 int ibx_array_download(ibx_ctx* c, ibx_array a, float* host);
+/* Asynchronous forms for hosts that keep the state in (pinned) host memory and pipeline independent evaluations, also on a
+ * rank-local shard (the sharded counterpart of ibx_euler_step_host_begin/_end):
+ *   upload_async   copies on the upload stream; everything enqueued afterwards on the compute / halo streams waits for it.
+ *                  The caller guarantees that no earlier work still reads `a` (e.g. by ibx_download_wait on its slot).
+ *   download_async copies on the download stream once the compute stream's work enqueued so far has finished.
+ *   download_fence marks the downloads enqueued so far as slot 0 / 1; download_wait blocks the host until they landed. */
+int ibx_array_upload_async(ibx_ctx* c, ibx_array a, const float* host);
+int ibx_array_download_async(ibx_ctx* c, ibx_array a, float* host);
+int ibx_download_fence(ibx_ctx* c, int slot);
+int ibx_download_wait(ibx_ctx* c, int slot);
 int ibx_array_fill(ibx_ctx* c, ibx_array a, float v);
 int ibx_array_copy(ibx_ctx* c, ibx_array dst, ibx_array src);
 int ibx_array_devptr(ibx_ctx* c, ibx_array a, void** ptr);

@@ -144,6 +144,10 @@ def test_accumulator_and_elementwise(ib, oracle):
     assert np.array_equal(ib.maximum(a, b).to_host(), np.maximum(v, v[::-1]))
     assert np.array_equal((1.0 / (a * a + 1.0)).to_host(), F32(1) / (v * v + F32(1)))
     assert np.isclose(a.sum(), v.astype(np.float64).sum()) and a.max() == v.max() and a.min() == v.min()
+    vn = v.copy()
+    vn[17, 1] = np.nan                                  # Julia's maximum / minimum propagate NaN: so do the reductions
+    an = ib.DeviceArray.from_host(vn)
+    assert np.isnan(an.max()) and np.isnan(an.min()) and np.isnan(an.sum())
     assert np.isclose(a.norm(), np.linalg.norm(v.astype(np.float64))) and a.maxabs() == np.abs(v).max()
     assert np.isclose(ib.dot(a, b), (v.astype(np.float64) * v[::-1]).sum())
     assert np.allclose(a.sum(per_column=True), v.astype(np.float64).sum(axis=0))
