@@ -1,6 +1,7 @@
 // Host mesher: block octree refinement and cell enumeration.
 // Mirrors src/mesher.jl:811-1112 of the reference (refine_octree, refine_orderly, Mesh, get_cells).
 #include "ibx_internal.h"
+#include <cstdio>
 
 #include <numeric>
 
@@ -115,6 +116,24 @@ void mesh_cells(const ibx_mesh& m, float* centers, float* widths) {
 
 using namespace ibx;
 
+namespace {
+const char kMeshMagic[8] = {'I', 'B', 'X', 'M', 'E', 'S', 'H', '1'};
+template <class T> void put(FILE* f, const T& v) { if (fwrite(&v, sizeof(T), 1, f) != 1) throw std::runtime_error("write failed"); }
+template <class T> void put_vec(FILE* f, const std::vector<T>& v) {
+  int64_t n = (int64_t)v.size();
+  put(f, n);
+  if (n && fwrite(v.data(), sizeof(T), (size_t)n, f) != (size_t)n) throw std::runtime_error("write failed");
+}
+template <class T> void get(FILE* f, T& v) { if (fread(&v, sizeof(T), 1, f) != 1) throw std::runtime_error("unexpected end of mesh file"); }
+template <class T> void get_vec(FILE* f, std::vector<T>& v) {
+  int64_t n;
+  get(f, n);
+  if (n < 0 || n > ((int64_t)1 << 40)) throw std::runtime_error("corrupt mesh file");
+  v.resize((size_t)n);
+  if (n && fread(v.data(), sizeof(T), (size_t)n, f) != (size_t)n) throw std::runtime_error("unexpected end of mesh file");
+}
+}  // namespace
+
 extern "C" {
 
 int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf, const ibx_surface* surfaces,
@@ -207,6 +226,104 @@ int ibx_mesh_from_blocks(const ibx_mesh* like, int block_size, ibx_mesh** out) {
   IBX_REQUIRE(block_size >= 1, "block_size must be positive");
   auto m = std::make_shared<ibx_mesh>(*src);
   m->block_size = block_size;
+  g_mesh[m.get()] = m;
+  *out = m.get();
+  return IBX_OK;
+  IBX_CATCH
+}
+
+// ---- mesh (de)serialisation.  In the reference a Mesh is plain data (src/mesher.jl:926-933) that Julia's `Serialization`
+// stdlib writes as is; behind this ABI it is an opaque handle, so the library writes it itself: header, root box, block
+// list, and per surface its name and refined STL (or the analytic-sphere parameters).  Distance fields (KD-trees) are
+// rebuilt on load, exactly as Mesh(...) builds them.
+
+int ibx_mesh_save(const ibx_mesh* mh, const char* path) {
+  IBX_TRY
+  auto m = lookup_mesh(mh);
+  FILE* f = fopen(path, "wb");
+  IBX_REQUIRE(f != nullptr, std::string("cannot open ") + path + " for writing");
+  try {
+    fwrite(kMeshMagic, 1, 8, f);
+    put(f, (int32_t)m->nd);
+    put(f, (int32_t)m->block_size);
+    for (int d = 0; d < 3; ++d) { put(f, m->origin[d]); put(f, m->widths[d]); }
+    put_vec(f, m->block_origins);
+    put_vec(f, m->block_widths);
+    put(f, (int32_t)m->surf_names.size());
+    for (size_t s = 0; s < m->surf_names.size(); ++s) {
+      std::vector<char> name(m->surf_names[s].begin(), m->surf_names[s].end());
+      put_vec(f, name);
+      const ibx_dfield& df = *m->surf_fields[s];
+      put(f, (int32_t)(df.sphere ? 1 : 0));
+      if (df.sphere) {
+        for (int d = 0; d < 3; ++d) put(f, df.sc[d]);
+        put(f, df.sr);
+      } else {
+        put(f, (int32_t)df.stl->nd);
+        put(f, (int32_t)(df.stl->f32 ? 1 : 0));
+        put_vec(f, df.stl->points);
+        put_vec(f, df.stl->simplices);
+      }
+    }
+  } catch (...) {
+    fclose(f);
+    throw;
+  }
+  fclose(f);
+  return IBX_OK;
+  IBX_CATCH
+}
+
+int ibx_mesh_load(const char* path, ibx_mesh** out) {
+  IBX_TRY
+  FILE* f = fopen(path, "rb");
+  IBX_REQUIRE(f != nullptr, std::string("cannot open ") + path);
+  auto m = std::make_shared<ibx_mesh>();
+  try {
+    char magic[8];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMeshMagic, 8) != 0) throw std::runtime_error(std::string(path) + " is not an ibx mesh file");
+    int32_t nd, bs, ns;
+    get(f, nd);
+    get(f, bs);
+    if (nd < 2 || nd > 3 || bs < 1) throw std::runtime_error("corrupt mesh file");
+    m->nd = nd;
+    m->block_size = bs;
+    for (int d = 0; d < 3; ++d) { get(f, m->origin[d]); get(f, m->widths[d]); }
+    get_vec(f, m->block_origins);
+    get_vec(f, m->block_widths);
+    if (m->block_origins.size() != m->block_widths.size() || m->block_origins.size() % nd) throw std::runtime_error("corrupt mesh file");
+    get(f, ns);
+    for (int s = 0; s < ns; ++s) {
+      std::vector<char> name;
+      get_vec(f, name);
+      m->surf_names.emplace_back(name.begin(), name.end());
+      int32_t sphere;
+      get(f, sphere);
+      std::shared_ptr<ibx_dfield> df;
+      if (sphere) {
+        df = std::make_shared<ibx_dfield>();
+        df->sphere = true;
+        for (int d = 0; d < 3; ++d) get(f, df->sc[d]);
+        get(f, df->sr);
+      } else {
+        auto stl = std::make_shared<ibx_stl>();
+        int32_t snd, f32;
+        get(f, snd);
+        get(f, f32);
+        stl->nd = snd;
+        stl->f32 = f32 != 0;
+        get_vec(f, stl->points);
+        get_vec(f, stl->simplices);
+        df = make_dfield(stl);
+      }
+      register_dfield(df);
+      m->surf_fields.push_back(df);
+    }
+  } catch (...) {
+    fclose(f);
+    throw;
+  }
+  fclose(f);
   g_mesh[m.get()] = m;
   *out = m.get();
   return IBX_OK;

@@ -246,6 +246,18 @@ class Mesh:
         """``Base.length(::Mesh)`` (``src/ImmersedBoundary.jl:47``)."""
         return self.ncells
 
+    def save(self, path):
+        """Write the mesh (root box, block list, surfaces with their refined STLs) to ``path`` (``ibx_mesh_save``): the
+        counterpart of serialising the reference's plain-data ``Mesh`` struct (``src/mesher.jl:926-933``)."""
+        call("ibx_mesh_save", self._h, str(path).encode())
+
+    @classmethod
+    def load(cls, path):
+        """Read a mesh written by ``save`` (``ibx_mesh_load``); distance fields are rebuilt."""
+        out = C.c_void_p()
+        call("ibx_mesh_load", str(path).encode(), C.byref(out))
+        return cls(_handle=out)
+
     def coarsened(self, block_size):
         """The positional constructor ``multigrid`` uses (``src/ImmersedBoundary.jl:1366-1368``)."""
         out = C.c_void_p()

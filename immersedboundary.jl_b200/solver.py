@@ -75,19 +75,22 @@ class PIPreconditioner:
         return out
 
 
-def hutchinson_trick(f, X, n_samples, h=1e-6, fX=None, rng=None):
+def hutchinson_trick(f, X, n_samples, h=1e-6, fX=None, rng=None, probes=None):
     """``hutchinson_trick`` (``src/point_implicit.jl:18-91``) -> D (N x nv*nv, block (p, j, i) at column j + nv*i).
 
-    Every probe is one full evaluation of ``f``; +-1 probes come from a counter-free NumPy generator seeded by
-    the caller (the reference uses the global RNG)."""
+    Every probe is one full evaluation of ``f``.  ``probes`` (n_samples, nv, N) of +-1 makes the estimate reproducible
+    and shard-independent (``synthetic.probe_signs``: counter-based, keyed by the global cell id); otherwise they come
+    from a NumPy generator seeded by the caller (the reference uses the global RNG).  Device arrays are Float32, so
+    unlike the reference -- whose Float64 default ``h = 1e-6`` promotes the whole evaluation to Float64
+     -- ``h`` must be resolvable in Float32 next to ``X`` (scale the unknowns)."""
     rng = rng or np.random.default_rng(0)
     fX = f(X) if fX is None else fX
     N, nv = X.rows, X.cols
     D = DeviceArray(N, nv * nv, False).fill(0.0)
     for i in range(nv):
         acc = DeviceArray(N, nv, False).fill(0.0)
-        for _ in range(n_samples):
-            z = rng.choice(np.array([-1.0, 1.0], dtype=F32), size=N)
+        for k in range(n_samples):
+            z = np.ascontiguousarray(probes[k, i], dtype=F32) if probes is not None else rng.choice(np.array([-1.0, 1.0], dtype=F32), size=N)
             dz = DeviceArray.from_host(z)
             Xb = X.copy()
             col = X.col(i) + dz * float(h)
@@ -111,11 +114,11 @@ class Linearization:
         return (self.f(self.x + v * self.h) - self.fx) / self.h
 
 
-def linearize(f, x, n_hutchinson_samples=30, pre_evaluated_fx=None, h=1e-6, rng=None):
+def linearize(f, x, n_hutchinson_samples=30, pre_evaluated_fx=None, h=1e-6, rng=None, probes=None):
     """``linearize`` (``src/point_implicit.jl:184-207``) -> (A, b, D)."""
     fx = f(x) if pre_evaluated_fx is None else pre_evaluated_fx.copy()
     x = x.copy()
-    D = hutchinson_trick(f, x, n_hutchinson_samples, h, fx, rng)
+    D = hutchinson_trick(f, x, n_hutchinson_samples, h, fx, rng, probes)
     return Linearization(f, x, fx, h), -fx, PIPreconditioner(D, x.cols)
 
 

@@ -70,3 +70,21 @@ def primitive2state_host(P, R=283.0, gamma=1.4):
     rho = P[:, 0] / (R * T)
     E = rho * (R / (gamma - F32(1.0)) * T + k)
     return np.concatenate([rho[:, None], E[:, None], rho[:, None] * u], axis=1).astype(F32)
+
+
+def probe_signs(global_ids, nv, n_samples, seed=0):
+    """+-1 Hutchinson probes from a counter-based generator keyed by (seed, sample, variable, GLOBAL cell id) -- a
+    splitmix64 finaliser of the key -- so that the probes of a cell do not depend on how the mesh is sharded over ranks
+    (the reference draws them from the global RNG stream, `src/point_implicit.jl:36`, which cannot be
+    split).  Returns float32 (n_samples, nv, len(global_ids))."""
+    g = np.asarray(global_ids, dtype=np.uint64)
+    out = np.empty((n_samples, nv, g.size), dtype=np.float32)
+    with np.errstate(over="ignore"):
+        for k in range(n_samples):
+            for v in range(nv):
+                z = g + np.uint64(0x9E3779B97F4A7C15) * np.uint64(1 + seed + 1000003 * (k * nv + v))
+                z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+                z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+                z = z ^ (z >> np.uint64(31))
+                out[k, v] = np.where((z >> np.uint64(63)) == 0, np.float32(1.0), np.float32(-1.0))
+    return out

@@ -106,6 +106,11 @@ int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf,
  * distance fields of `like` */
 int ibx_mesh_from_blocks(const ibx_mesh* like, int block_size, ibx_mesh** out);
 int ibx_mesh_free(ibx_mesh* m);
+/* Mesh (de)serialisation: a Mesh is plain data in the reference (src/mesher.jl:926-933; Julia's `Serialization` stdlib
+ * writes it as is); behind this ABI it is an opaque handle, so the library writes / reads it itself (root box, block list,
+ * per surface its name and refined STL or analytic-sphere parameters; distance fields are rebuilt on load). */
+int ibx_mesh_save(const ibx_mesh* m, const char* path);
+int ibx_mesh_load(const char* path, ibx_mesh** out);
 int ibx_mesh_info(const ibx_mesh* m, int* nd, int* block_size, int64_t* nblocks, int64_t* ncells, int* nsurf);
 int ibx_mesh_blocks(const ibx_mesh* m, float* block_origins, float* block_widths);     /* nblocks x nd row-major */
 int ibx_mesh_surface_name(const ibx_mesh* m, int i, const char** name);

@@ -156,3 +156,64 @@ def test_2d_residual_is_independent_of_earlier_calls(get_case, ib):
     del junk
     b = run2()
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (int((a[0] != b[0]).sum()), float(np.nanmax(np.abs(a[0] - b[0]))))
+
+
+def test_point_implicit_on_the_euler_residual_vs_oracle(get_case, ib, oracle):
+    """hutchinson_trick / linearize / proj_along / solve (src/point_implicit.jl:18-91, 184-233, 250-329) driven by the Euler
+    residual + IB ghost update of C3 on the device, next to oracle/point_implicit.py doing the same with the same
+    counter-based +-1 probes (synthetic.probe_signs, keyed by the global cell id).  Unknowns are scaled to O(1) so that the
+    finite-difference step is resolvable in Float32 (the reference's Float64 `h = 1e-6` would promote the evaluation)."""
+    from oracle import point_implicit as opi
+    c = get_case("rae2822", 10_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    N, nv = len(c.dom), 4
+    a_inf = np.sqrt(1.4 * 283.0 * 288.15)
+    d = ib.streamwise_direction(ALPHA)
+    Pinf = np.array([101325.0, 288.15, MACH * a_inf * d[0], MACH * a_inf * d[1]], F32)
+    wall = np.array([101325.0, 288.15, 0.0], F32)
+    bcs = [("wall", ib.FlowBC(fl, wall, normal_flow=True)), ("farfield", ib.FlowBC(fl, Pinf))]
+    obcs = [("wall", cfd.FlowBC(ofl, wall, normal_flow=True)), ("farfield", cfd.FlowBC(ofl, Pinf))]
+    P0 = ib.synthetic.euler_state(c.odom.centers, mach=MACH)
+    Q0 = ib.synthetic.primitive2state_host(P0)
+    scale = np.abs(Q0).max(axis=0).astype(F32)
+    X0 = (Q0 / scale).astype(F32)
+    S = ib.DeviceArray.from_host(np.tile(scale, (N, 1)))
+    h = F32(2e-3)
+
+    def f(X):                                   # pseudo-time increment of the scaled unknowns
+        Qg = X * S
+        ib.ghost_update_euler(c.dom, fl, Qg, bcs)
+        R, cf = ib.DeviceArray(N, nv, False), ib.DeviceArray(N, 1, True)
+        ib.residual_euler(c.dom, fl, Qg, R, cf)
+        return R * (float(CFL) / cf) / S
+
+    def fo(X):
+        Qg = (X * scale).astype(F32)
+        E.euler_ghost_update(c.odom, ofl, Qg, obcs)
+        R, cf = np.zeros_like(Qg), np.zeros(N, F32)
+        c.odom(E.euler_residual(ofl), Qg, R, cf)
+        return (R * (CFL / cf)[:, None] / scale).astype(F32)
+
+    n_samples = 2
+    probes = ib.synthetic.probe_signs(np.arange(N), nv, n_samples, seed=3)
+    X = ib.DeviceArray.from_host(X0)
+    fX, foX = f(X), fo(X0)
+    fs = np.abs(foX).max()
+    assert np.abs(fX.to_host() - foX).max() < 2e-4 * fs          # ghost-weight roundings amplified by the residual
+    D = ib.hutchinson_trick(f, X, n_samples, h=h, fX=fX, probes=probes).to_host().reshape(N, nv, nv).transpose(0, 2, 1)
+    Do = opi.hutchinson_trick(fo, X0, n_samples, h, foX, probes=probes)        # D[p, j, i]
+    ds = np.abs(Do).max()
+    # finite differences divide the Float32 rounding of f by h: agreement to ~1e-7 |f| / h
+    assert np.abs(D - Do).max() < 2e-2 * ds, (np.abs(D - Do).max(), ds)
+    assert np.median(np.abs(D - Do)) < 1e-4 * ds
+    lin, b, pre = ib.linearize(f, X, n_hutchinson_samples=n_samples, pre_evaluated_fx=fX, h=h, probes=probes)
+    olin, ob, opre = opi.linearize(fo, X0, n_samples, foX, h, probes=probes)
+    v = (probes[0].T * F32(0.01)).astype(F32)
+    Av, oAv = lin(ib.DeviceArray.from_host(v)).to_host(), olin(v)
+    assert np.abs(Av - oAv).max() < 2e-2 * np.abs(oAv).max()
+    dx, ratio = ib.solve(lin, b, pre, n_iter=3, rtol=1e-6)
+    odx, oratio = opi.solve(olin, ob, opre, n_iter=3, rtol=F32(1e-6))
+    assert np.isfinite(dx.to_host()).all()
+    assert abs(float(ratio) - float(oratio)) < 5e-2 * max(float(oratio), 1e-3), (ratio, oratio)
+    assert float(ratio) < 1.0                                     # the preconditioned projection steps reduce the residual

@@ -5,6 +5,7 @@ import os
 import xml.etree.ElementTree as ET
 
 import numpy as np
+import pytest
 
 F32 = np.float32
 
@@ -62,3 +63,31 @@ def test_surface_grid_of_a_stereolitography(ib, tmp_path):
     assert np.array_equal(_arr(named["cellval"]).astype(F32), val)
     # a closed 2-D curve has as many segments as points: WriteVTK-style length matching cannot tell the two apart
     assert np.array_equal(_arr(named["xy"]).astype(F32).reshape(-1, 2), pts.astype(F32))
+
+
+def test_mesh_save_load_round_trip(ib, tmp_path):
+    """Mesh (de)serialisation: a saved and re-loaded mesh gives the same blocks, cells, refined STL and
+    -- through rebuilt distance fields -- the same Domain tables (ghosts, donors, weights), 2-D STL and 3-D analytic."""
+    import os
+    rae = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rae2822.dat")
+    stl = ib.merge_points(ib.Stereolitography(rae))
+    m2 = ib.Mesh(np.array([-25, -25], np.float32), np.array([50, 50], np.float32), ("wall", stl, np.float32(2e-2)))
+    m3 = ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Sphere([0, 0, 0], 0.5), np.float32(0.12)))
+    for k, (m, fams) in enumerate(((m2, [("farfield", [(0, False), (0, True), (1, False), (1, True)])]),
+                                   (m3, [("farfield", [(d, s) for d in range(3) for s in (False, True)])]))):
+        path = tmp_path / f"mesh{k}.ibx"
+        m.save(path)
+        r = ib.Mesh.load(path)
+        assert (r.nd, r.block_size, r.nblocks, r.ncells) == (m.nd, m.block_size, m.nblocks, m.ncells)
+        assert np.array_equal(r.block_origins, m.block_origins) and np.array_equal(r.block_widths, m.block_widths)
+        assert sorted(r.distance_fields) == sorted(m.distance_fields)
+        da = ib.Domain(m, hypercube_families=fams, upload=False)
+        db = ib.Domain(r, hypercube_families=fams, upload=False)
+        assert np.array_equal(da.faces(), db.faces())
+        for name in da.boundaries:
+            for key, b in da.boundaries[name].items():
+                c = db.boundaries[name][key]
+                assert np.array_equal(b.ghost_indices, c.ghost_indices) and np.array_equal(b.projections, c.projections)
+                assert np.array_equal(b.image_domain, c.image_domain) and np.array_equal(b.interp_w, c.interp_w)
+    with pytest.raises(ib.IbxError):
+        ib.Mesh.load(rae)                      # not a mesh file
