@@ -547,6 +547,222 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- C5 (secondary workload)
+def build_wing_mesh(ib, level, margin):
+    """C5 recipe: same box as C4, wall = procedurally generated swept wing (NACA 0012 section, span 4, sweep
+    30 degrees) as an STL refined by the reference's rule, finest cells inside a box `margin` around the wing."""
+    pts, tri = ib.synthetic.swept_wing()
+    h = F32(32.0 / 2 ** level / 8 * 1.01)
+    lo = pts.min(axis=0) - margin
+    w = pts.max(axis=0) - pts.min(axis=0) + 2 * margin
+    return ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", ib.Stereolitography(pts, tri), h),
+                   refinement_regions=[(ib.Box(lo.tolist(), w.tolist()), h)])
+
+
+def run_c5(args):
+    """`--workload c5`: 3-D wing RANS residual (Euler part + viscous fluxes with the Wray-Agarwal eddy viscosity + transported-R
+    residual, ibx_residual_rans) + IB ghost updates of the mean flow and of R, ~25 M cells per GPU (200 M on 8)."""
+    import immersedboundary_jl_b200 as ib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        try:
+            C.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 8) // world))
+        except OSError:
+            pass
+    ctx = ib.context(local_rank)
+    t_setup = time.perf_counter()
+    target = args.cells if args.cells else 25_000_000 * world
+    level = args.level if args.level != 10 or target > 60_000_000 else 9
+    # smallest margin (1/64 grid) whose mesh reaches the target
+    lo_m, hi_m = 0.0, 1.0
+    for _ in range(6):
+        mid = round((lo_m + hi_m) / 2 * 64) / 64
+        if mid in (lo_m, hi_m):
+            break
+        if len(build_wing_mesh(ib, level, mid)) >= target:
+            hi_m = mid
+        else:
+            lo_m = mid
+    msh = build_wing_mesh(ib, level, hi_m)
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    gdom = ib.Domain(msh, max_partition_size=len(msh), hypercube_families=fams, build_partitions=False, build_surfaces=False,
+                     upload=False, for_rank=(rank, world) if world > 1 else None)
+    n_global = len(gdom)
+    if world > 1:
+        def gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        dom = gdom.shard(rank, world, all_gather_object=gather)
+        ident = np.zeros(128, np.uint8)
+        if rank == 0:
+            ib._lib.call("ibx_comm_unique_id", ib._lib.ptr(ident))
+        obj = [ident.tobytes()]
+        dist.broadcast_object_list(obj, src=0)
+        ib._lib.call("ibx_comm_init", ctx, rank, world, ib._lib.ptr(np.frombuffer(obj[0], np.uint8).copy()))
+        n_owned = dom.shard_info["n_owned"]
+        del gdom
+    else:
+        dom, n_owned = gdom, n_global
+    centers = dom.cells()[0]
+    dom.upload()
+    n_local = len(dom)
+    fluid = ib.Fluid()
+    a_inf = math.sqrt(1.4 * 283.0 * 288.15)
+    Pinf = np.array([101325.0, 288.15, 0.5 * a_inf, 0.0, 0.0], F32)
+    bcs = [("wall", ib.FlowBC(fluid, np.array([101325.0, 288.15, 0.0], F32), normal_flow=True)), ("farfield", ib.FlowBC(fluid, Pinf))]
+    nu_inf = 1.79e-5 / (101325.0 / (283.0 * 288.15))
+    rbc = [("wall", 0.0), ("farfield", 3.0 * nu_inf)]              # `R_inf = 3 nu`, `R = 0` at walls (src/turbulence.jl:203)
+    Q_host = ib.pinned_empty((n_local, 5))
+    Q_host[...] = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(centers))
+    q_host = ib.pinned_empty((n_local,))
+    q_host[...] = Q_host[:, 0] * F32(3.0 * nu_inf) * (1 + F32(0.2) * np.sin(centers[:, 0]).astype(F32))
+    del centers
+    Q, qR = ib.DeviceArray(n_local, 5, False).upload(Q_host), ib.DeviceArray(n_local, 1, True).upload(q_host)
+    R, RR, cfl = ib.DeviceArray(n_local, 5, False), ib.DeviceArray(n_local, 1, True), ib.DeviceArray(n_local, 1, True)
+    n_ghost = sum(b.nghost for bs in dom.boundaries.values() for b in bs.values())
+    setup_s = time.perf_counter() - t_setup
+
+    def step():
+        if world > 1:
+            dom.halo_exchange(Q)
+            dom.halo_exchange(qR)
+        ib.ghost_update_euler(dom, fluid, Q, bcs)
+        ib.ghost_update_rans(dom, Q, qR, rbc)
+        if world > 1:
+            dom.halo_exchange(Q)
+            dom.halo_exchange(qR)
+        ib.residual_rans(dom, fluid, Q, qR, R, RR, cfl)
+
+    def barrier():
+        ib.synchronize()
+        if world > 1:
+            dist.barrier()
+        ib.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ib.launch_count()
+    ms = C.c_float()
+    sampler.mark_begin()
+    ib._lib.call("ibx_timer_start", ctx)
+    for _ in range(args.steps):
+        step()
+    ib._lib.call("ibx_timer_stop", ctx, C.byref(ms))
+    sampler.mark_end()
+    barrier()
+    launches = ib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ms.value
+    if world > 1:
+        import torch
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    # end to end with host buffers: upload Q and qR, step, download R, RR, cfl (serial form)
+    R_host, RR_host, c_host = ib.pinned_empty((n_local, 5)), ib.pinned_empty((n_local,)), ib.pinned_empty((n_local,))
+    k = max(2, min(args.steps, 4))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        Q.upload(Q_host)
+        qR.upload(q_host)
+        step()
+        for a, hbuf in ((R, R_host), (RR, RR_host), (cfl, c_host)):
+            ib._lib.call("ibx_array_download", ctx, a.h, ib._lib.ptr(hbuf))
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        ib._lib.call("ibx_comm_finalize", ctx)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = measured_peak_gbs()
+    b_alg = 4 * (2 * 6 + 1)                         # 52 B per cell-update (SURVEY.md 8d, nv = 6)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_c5()
+    line = {
+        "metric": "cell-updates/s (RANS residual+IB)", "value": n_global * args.steps / (ms_total * 1e-3), "unit": "cell-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5: 3-D swept-wing RANS residual (Euler part: MUSCL + JST + HLL; viscous fluxes with the Wray-Agarwal eddy "
+                               "viscosity; transported-R residual) + IB ghost updates (mean flow and R); wall = procedural NACA 0012 wing STL, "
+                               "span 4, sweep 30 deg", "cells": n_global, "cells_per_gpu": n_owned, "ghost_cells_rank0": n_ghost,
+                   "blocks": msh.nblocks, "finest_level": level, "refinement_margin": hi_m, "block_size": 8, "nv": 6,
+                   "l2": "working set >> 126 MB L2, no flush needed", "setup_s": round(setup_s, 1)},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": n_global * k / dt, "unit": "cell-updates/s", "h2d_bytes_per_step": int(Q_host.nbytes + q_host.nbytes) * world,
+                "d2h_bytes_per_step": int(R_host.nbytes + RR_host.nbytes + c_host.nbytes) * world, "ms_per_step": dt / k * 1e3, "steps": k,
+                "api": "ibx_array_upload + sharded RANS step + ibx_array_download (C ABI, pinned host buffers)"},
+        "roofline": {"bound": "hbm", "achieved": n_owned * b_alg / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": n_owned * b_alg / (ms_step * 1e-3) / 1e9 / peak, "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "whole step: ibx_residual_euler kernels + k_rans_state / _grad / _source / _flux + ghost updates",
+                     "algorithmic_bytes_per_cell": b_alg},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_c5():
+    """The restated RANS composition (NumPy oracle; no compiled port of the viscous / turbulence operators exists) on a
+    bounded sample: the same wing recipe at octree level 5."""
+    import oracle
+    from oracle import cfd as ocfd, euler as oeuler
+    from immersedboundary_jl_b200 import synthetic
+    OM = oracle.mesher
+    cores = os.cpu_count() or 1
+    pts, tri = synthetic.swept_wing(n_chord=32, n_span=32)
+    h = F32(32.0 / 2 ** 5 / 8 * 1.01)
+    lo, w = pts.min(axis=0) - 0.05, pts.max(axis=0) - pts.min(axis=0) + 0.1
+    msh = OM.Mesh([-16, -16, -16], [32, 32, 32], ("wall", OM.Stereolitography(pts, tri), h), refinement_regions=[(OM.Box(lo.tolist(), w.tolist()), h)])
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    dom = oracle.domain.Domain(msh, max_partition_size=max(4096, len(msh) // cores + 1), hypercube_families=fams)
+    fl = ocfd.Fluid()
+    a = np.sqrt(1.4 * 283.0 * 288.15)
+    Pinf = np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)
+    bcs = [("wall", ocfd.FlowBC(fl, Pinf[:3] * np.array([1, 1, 0], F32), normal_flow=True)), ("farfield", ocfd.FlowBC(fl, Pinf))]
+    Q = synthetic.primitive2state_host(synthetic.euler_state(dom.centers))
+    qR = (Q[:, 0] * F32(4.5e-5)).astype(F32)
+    R, RR, cf = np.zeros_like(Q), np.zeros(len(Q), F32), np.zeros(len(Q), F32)
+    res = oeuler.rans_residual(fl)
+    n = len(Q)
+
+    def step():
+        oeuler.euler_ghost_update(dom, fl, Q, bcs)
+        oeuler.rans_ghost_update(dom, Q, qR, [("wall", 0.0), ("farfield", 4.5e-5)])
+        dom(res, Q, qR, R, RR, cf, n_threads=cores)
+
+    step()
+    t0 = time.perf_counter()
+    steps = 3
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"NumPy restatement of the reference operators composed as oracle/euler.py: rans_residual (Julia cannot run here), the "
+                      f"wing recipe at octree level 5 -> {n} cells in {len(dom.partitions)} partitions, {steps} evaluations, {cores} threads"}
+
+
 if __name__ == "__main__":
     import ctypes as C
     ap = argparse.ArgumentParser()
@@ -554,6 +770,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"], help="c4 = the headline sphere Euler workload; c5 = wing RANS")
     ap.add_argument("--cells", type=int, default=0, help="override the target cell count (debugging)")
     ap.add_argument("--radius", type=float, default=0.0, help="override the refinement-ball radius (debugging)")
     ap.add_argument("--level", type=int, default=10, help="finest octree level (10 = the C4 workload; lower for smoke runs)")
@@ -563,5 +780,7 @@ if __name__ == "__main__":
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)

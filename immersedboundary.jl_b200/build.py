@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
         op = os.path.join(OBJ, src + ".o")
         if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hm):
             # march_fast.cu (option "arithmetic" = 1) is the one numerical TU compiled WITH contraction
-            extra = NOFMA if src in ("ops.cu", "cfd.cu", "fused.cu", "tile.cu", "march.cu", "closures.cu", "gen.cu") else []
+            extra = NOFMA if src in ("ops.cu", "cfd.cu", "fused.cu", "tile.cu", "march.cu", "closures.cu", "gen.cu", "rans.cu") else []
             cmd = [NVCC] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
             if src.endswith(".cpp"):
                 cmd = [NVCC] + COMMON + ["-x", "cu"] * 0 + ["-c", sp, "-o", op]

@@ -182,6 +182,23 @@ def residual_euler(dom, fluid, Q, R, cfl, flux="hll"):
     call("ibx_residual_euler", context(), dom._h, fluid.c, 0 if flux == "hll" else 1, Q.h, R.h, cfl.h)
 
 
+def residual_rans(dom, fluid, Q, qR, R, RR, cfl, sigma_R=0.72, C1=0.0829, kappa=0.41):
+    """Canonical RANS residual of configuration C5 (``ibx_residual_rans``): ``R, cfl`` = Euler residual + viscous fluxes
+    with the Wray-Agarwal eddy viscosity, ``RR`` = residual of the transported ``qR = rho R`` (``src/cfd.jl:664-736``,
+    ``src/turbulence.jl:197-241``; composition: ``oracle/euler.py: rans_residual``)."""
+    dom.upload()
+    call("ibx_residual_rans", context(), dom._h, fluid.c, fluid.transport, float(sigma_R), float(C1), float(kappa),
+         Q.h, qR.h, R.h, RR.h, cfl.h)
+
+
+def ghost_update_rans(dom, Q, qR, R_bcs):
+    """IB ghost update of the transported Wray-Agarwal variable for ``R_bcs = [(boundary name, R value), ...]`` in order
+    (``ibx_ghost_update_rans``); call after ``ghost_update_euler`` (it uses the ghost densities)."""
+    dom.upload()
+    for name, val in R_bcs:
+        call("ibx_ghost_update_rans", context(), dom._h, dom.boundary_index[name], Q.h, qR.h, float(val))
+
+
 def ghost_update_euler(dom, fluid, Q, bcs):
     """IB ghost update of the conservative state for ``bcs = [(boundary name, FlowBC), ...]`` in order."""
     dom.upload()

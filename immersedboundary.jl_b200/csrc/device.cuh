@@ -33,6 +33,10 @@ struct ibx_ctx {
   int64_t scratch_cap = 0;
   float* d_scratch2 = nullptr;  // fluxes of the general faces of irregular blocks (two-pass hybrid kernel)
   int64_t scratch2_cap = 0;
+  float* d_scratch3 = nullptr;  // C5: primitives + R, cell gradients, shear rate / nu_eff, source (rans.cu)
+  int64_t scratch3_cap = 0;
+  float* d_scratch4 = nullptr;  // C5: ghost staging of the transported variable
+  int64_t scratch4_cap = 0;
   // end-to-end staging arrays
   // two slots: the copies of one call overlap the compute / opposite-direction copies of the other (PCIe is full duplex)
   struct E2ESlot {

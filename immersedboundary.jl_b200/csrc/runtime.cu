@@ -114,6 +114,8 @@ int ibx_finalize(ibx_ctx* c) {
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_scratch2) cudaFree(c->d_scratch2);
+  if (c->d_scratch3) cudaFree(c->d_scratch3);
+  if (c->d_scratch4) cudaFree(c->d_scratch4);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);

@@ -88,3 +88,37 @@ def probe_signs(global_ids, nv, n_samples, seed=0):
                 z = z ^ (z >> np.uint64(31))
                 out[k, v] = np.where((z >> np.uint64(63)) == 0, np.float32(1.0), np.float32(-1.0))
     return out
+
+
+def swept_wing(n_chord=64, n_span=64, chord=1.0, span=4.0, sweep_deg=30.0, thickness=0.12):
+    """Procedural wing of SURVEY.md 8(d) for configuration C5: a NACA 00xx section (closed trailing edge) extruded along z
+    over `span` with `sweep_deg` of sweep, closed by two tip caps -> (points (n, 3) float32, triangles (m, 3) int64).
+    The wing is centred on z = 0; the root leading edge sits at x = -span / 2 * tan(sweep)."""
+    beta = np.linspace(0.0, np.pi, n_chord + 1)
+    x = 0.5 * (1.0 - np.cos(beta))                               # cosine spacing, x[0] = 0 (LE), x[-1] = 1 (TE)
+    y = 5.0 * thickness * (0.2969 * np.sqrt(x) - 0.1260 * x - 0.3516 * x ** 2 + 0.2843 * x ** 3 - 0.1036 * x ** 4)
+    y[0] = y[-1] = 0.0
+    # section loop: TE -> upper -> LE -> lower -> (TE): 2 * n_chord distinct points
+    sx = np.concatenate([x[::-1], x[1:-1]]) * chord
+    sy = np.concatenate([y[::-1], -y[1:-1]]) * chord
+    m = len(sx)
+    zs = np.linspace(-span / 2, span / 2, n_span + 1)
+    tan_s = np.tan(np.radians(sweep_deg))
+    pts = np.concatenate([np.stack([sx + z * tan_s, sy, np.full(m, z)], axis=1) for z in zs])
+    tri = []
+    for k in range(n_span):
+        a, b = k * m, (k + 1) * m
+        for i in range(m):
+            j = (i + 1) % m
+            tri += [[a + i, a + j, b + j], [a + i, b + j, b + i]]
+    # tip caps: strips between the upper point U_k and the lower point L_k of the same chord station
+    up = lambda k: n_chord - k                                   # index of U_k in the loop (U_n = TE at 0, U_0 = LE at n_chord)
+    lo = lambda k: n_chord + k if 0 < k < n_chord else up(k)     # L_k (L_0 = LE, L_n = TE coincide with U_0, U_n)
+    for base, flip in ((0, False), (n_span * m, True)):
+        for k in range(n_chord):
+            quad = [base + up(k), base + up(k + 1), base + lo(k + 1), base + lo(k)]
+            ts = [[quad[0], quad[1], quad[2]], [quad[0], quad[2], quad[3]]]
+            for t in ts:
+                if len(set(t)) == 3:
+                    tri.append(t[::-1] if flip else t)
+    return pts.astype(F32), np.asarray(tri, dtype=np.int64)

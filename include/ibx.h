@@ -359,6 +359,18 @@ int ibx_residual_advection(ibx_ctx* c, const ibx_domain* d, ibx_array u, ibx_arr
 /* Canonical Euler residual: Q -> (R, cfl).  flux_kind 0 = HLL, 1 = sensor-Rusanov. */
 int ibx_residual_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, ibx_array Q, ibx_array R,
                        ibx_array cfl);
+/* Configuration C5 -- canonical RANS residual (ours: the reference ships the pieces, not a composition; oracle/euler.py
+ * rans_residual states it with the restated operators).  Q: ncells x 5 mean-flow state, qR = rho * R: the transported
+ * Wray-Agarwal variable (src/turbulence.jl:197-241, nu_t = R).  R, cfl = ibx_residual_euler (HLL) plus, per dimension,
+ * green_gauss(viscous_fluxes(at_faces(P), face_gradient(P, dim, cell_gradient(P)), dim; mu_t = at_faces(rho R)))
+ * (src/cfd.jl:664-736, src/ImmersedBoundary.jl:1039-1069); RR = div[rho (nu + sigma_R R) grad R] - div(rho u R) (upwind on
+ * MUSCL states) + rho S_WA(R, shear_rate(grad u), grad R, grad shear_rate).  3-D; runs on rank-local shards as well. */
+int ibx_residual_rans(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, ibx_transport t, float sigma_R, float C1, float kappa,
+                      ibx_array Q, ibx_array qR, ibx_array R, ibx_array RR, ibx_array cfl);
+/* IB ghost update of the transported variable of C5 for boundary b: impose_bc!(dom, b, R) do ...; R_bc end on R = qR / rho
+ * (src/ImmersedBoundary.jl:1197-1247; `R = 0` at walls, `R_inf = 3 nu` in the far field, src/turbulence.jl:203), written back
+ * as rho_ghost * R_ghost.  Call after ibx_ghost_update_euler of the same boundary (it needs the ghost densities). */
+int ibx_ghost_update_rans(ibx_ctx* c, const ibx_domain* d, int b, ibx_array Q, ibx_array qR, float R_bc);
 /* IB ghost update on the conservative state for boundary b with FlowBC(fluid, Pinf; normal_flow):
  * image interpolation of P = state2primitive(Q), BC, eta-blend, primitive2state, written Jacobi-style. */
 int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, const float* Pinf, int n_pinf,

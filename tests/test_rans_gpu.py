@@ -1,0 +1,69 @@
+"""Configuration C5 (BASELINE.json configs[4]): the canonical RANS residual -- Euler part + viscous fluxes with the
+Wray-Agarwal eddy viscosity + the transported-R residual -- on the device (ibx_residual_rans: fused Euler kernels +
+table-free viscous / turbulence kernels, rans.cu) against the oracle composition of the restated reference operators
+(oracle/euler.py: rans_residual).  A deliberately viscous fluid (mu_ref 2e-2) makes the viscous terms as large as the
+inviscid ones, so that the tolerance means something for them."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.mark.parametrize("name,mps", [("sphere3d_stl", 100_000), ("sphere3d", 40_000)])
+def test_rans_residual_against_oracle(get_case, ib, oracle, name, mps):
+    c = get_case(name, mps, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl = ib.Fluid(mu_ref=2e-2)
+    ofl = cfd.Fluid(mu_ref=F32(2e-2))
+    od = c.odom
+    N = len(od.centers)
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(od.centers))
+    x = od.centers
+    qR0 = (Q0[:, 0] * F32(3e-2) * (1 + F32(0.3) * np.sin(F32(2) * x[:, 0]) * np.cos(F32(3) * x[:, 1]))).astype(F32)
+    Ro, RRo, co = np.zeros_like(Q0), np.zeros(N, F32), np.zeros(N, F32)
+    od(E.rans_residual(ofl), Q0.copy(), qR0.copy(), Ro, RRo, co)
+    Re, ce = np.zeros_like(Q0), np.zeros(N, F32)
+    od(E.euler_residual(ofl), Q0.copy(), Re, ce)
+    Q, qR = ib.DeviceArray.from_host(Q0), ib.DeviceArray.from_host(qR0)
+    R, RR, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True), ib.DeviceArray(N, 1, True)
+    ib.residual_rans(c.dom, fl, Q, qR, R, RR, cf)
+    Rg, RRg, cg = R.to_host(), RR.to_host(), cf.to_host()
+    assert np.array_equal(cg, co)
+    # the viscous increment on its own (the Euler part is bit-exact, tests/test_fused_gpu.py)
+    dv, dvo = Rg - Re, Ro - Re
+    vs = np.abs(dvo).max(axis=0)
+    assert (vs[1:] > 1e-3 * np.abs(Re).max(axis=0)[1:]).all()                 # the viscous terms are not negligible here
+    assert np.array_equal(Rg[:, 0], Ro[:, 0])                                   # no viscous mass flux
+    err = np.abs(dv[:, 1:] - dvo[:, 1:]) / vs[1:]
+    assert err.max() < 1e-5, err.max(axis=0)
+    rs = np.abs(RRo).max()
+    assert rs > 0 and np.abs(RRg - RRo).max() < 1e-5 * rs, (np.abs(RRg - RRo).max(), rs)
+    # whole residual under the north-star tolerance (flux-scaled)
+    from bench import flux_scaled_error
+    assert flux_scaled_error(od.widths, Q0, Rg, Ro).max() < 1e-5
+
+
+def test_rans_ghost_update_against_oracle(get_case, ib, oracle):
+    c = get_case("sphere3d", 40_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(), cfd.Fluid()
+    od = c.odom
+    N = len(od.centers)
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(od.centers))
+    qR0 = (Q0[:, 0] * F32(3e-4) * (1 + F32(0.3) * np.sin(F32(2) * od.centers[:, 0]))).astype(F32)
+    a = np.sqrt(1.4 * 283.0 * 288.15)
+    Pinf = np.array([101325.0, 288.15, 0.5 * a, 0.0, 0.0], F32)
+    wall = np.array([101325.0, 288.15, 0.0], F32)
+    bcs = [("wall", ib.FlowBC(fl, wall, normal_flow=True)), ("farfield", ib.FlowBC(fl, Pinf))]
+    obcs = [("wall", cfd.FlowBC(ofl, wall, normal_flow=True)), ("farfield", cfd.FlowBC(ofl, Pinf))]
+    rbc = [("wall", 0.0), ("farfield", 4.5e-5)]
+    Q, qR = ib.DeviceArray.from_host(Q0), ib.DeviceArray.from_host(qR0)
+    ib.ghost_update_euler(c.dom, fl, Q, bcs)
+    ib.ghost_update_rans(c.dom, Q, qR, rbc)
+    Qo, qRo = Q.to_host(), qR0.copy()          # the oracle continues from the SAME ghost-updated mean-flow state
+    E.rans_ghost_update(od, Qo, qRo, rbc)
+    got = qR.to_host()
+    changed = np.flatnonzero(qRo != qR0)
+    assert len(changed) > 1000 and np.array_equal(np.flatnonzero(got != qR0), changed)
+    assert np.abs(got - qRo).max() < 2e-6 * np.abs(qRo).max()      # interpolation weights: float32 SVD vs double Jacobi
