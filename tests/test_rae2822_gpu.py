@@ -195,12 +195,29 @@ def test_point_implicit_on_the_euler_residual_vs_oracle(get_case, ib, oracle):
         c.odom(E.euler_residual(ofl), Qg, R, cf)
         return (R * (CFL / cf)[:, None] / scale).astype(F32)
 
+    # Ghost-interpolation weights agree to ~2e-6 only (float32 SVD in the oracle, double Jacobi in the product) and the
+    # residual amplifies that by ~1e3 next to the body: give the oracle the product's weights (donor sets are identical,
+    # tests/test_builder_parity.py) so that the comparison below is about the solver chain, not about pinv roundings.
+    saved = {}
+    for bname, chunks in c.odom.boundaries.items():
+        for k, ob in chunks.items():
+            b = c.dom.boundaries[bname][k]
+            saved[(bname, k)] = ob.image_interpolator
+            ob.image_interpolator = oracle.accumulator.Accumulator.from_csr(b.interp_ptr, b.interp_idx, b.interp_w)
+    try:
+        _point_implicit_body(ib, oracle, opi, f, fo, X0, N, nv, h)
+    finally:
+        for (bname, k), acc in saved.items():
+            c.odom.boundaries[bname][k].image_interpolator = acc
+
+
+def _point_implicit_body(ib, oracle, opi, f, fo, X0, N, nv, h):
     n_samples = 2
     probes = ib.synthetic.probe_signs(np.arange(N), nv, n_samples, seed=3)
     X = ib.DeviceArray.from_host(X0)
     fX, foX = f(X), fo(X0)
     fs = np.abs(foX).max()
-    assert np.abs(fX.to_host() - foX).max() < 2e-4 * fs          # ghost-weight roundings amplified by the residual
+    assert np.abs(fX.to_host() - foX).max() < 1e-5 * fs
     D = ib.hutchinson_trick(f, X, n_samples, h=h, fX=fX, probes=probes).to_host().reshape(N, nv, nv).transpose(0, 2, 1)
     Do = opi.hutchinson_trick(fo, X0, n_samples, h, foX, probes=probes)        # D[p, j, i]
     ds = np.abs(Do).max()
