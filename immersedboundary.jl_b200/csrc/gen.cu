@@ -3,7 +3,7 @@
 // block whose 4-cell stencil leaves the uniform lattice.  They are 2.5 % of the faces of the C4 mesh; the generic
 // neighbour-list code that used to evaluate them (k_hyb_flux MODE 1, tile.cu) took 17 % of the step.
 //
-// One CTA per irregular block, one thread per pencil of an irregular face (64 per dimension); no shared memory, no barrier: a thread
+// Three CTAs of 64 threads per irregular block (one per dimension, one thread per pencil of an irregular face); no shared memory, no barrier: a thread
 // reads the three own cells behind the face and the halo cells in front of it straight from global memory (each is
 // read by at most four threads; L1 absorbs that) and evaluates, with the arithmetic and the operation order of the
 // reference (weights 1/len, products first, sums in list order: src/accumulator.jl:95-106, at_faces :899-910,
@@ -61,13 +61,15 @@ __device__ __forceinline__ void face_flux(ibx_fluid fl, int d, const CellVals& O
 }
 
 template <int FLUX, bool FINER>
-__global__ void __launch_bounds__(3 * FACE)
+__global__ void __launch_bounds__(FACE)
 k_gen_faces(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ faces, const float* __restrict__ bh, int64_t N,
             ibx_fluid fl, const float* __restrict__ P, const float* __restrict__ Dg, double* __restrict__ GF, float* __restrict__ GC) {
   constexpr int NX = FINER ? 2 * FACE * 4 : 0, NSL = 4 * FACE + NX;
-  const int64_t b = blocks[blockIdx.x];
-  // 192 threads: one group of 64 (one thread per pencil) per dimension, each walking the low and the high block face
-  const int grp = threadIdx.x >> 6, pen = threadIdx.x & 63, t1 = pen & 7, t2 = pen >> 3;
+  // three CTAs of 64 threads per block, one per dimension (one thread per pencil), each walking the low and the high block
+  // face: a CTA whose dimension has no irregular face exits at once and frees its registers for the others
+  const int blk = blockIdx.x / 3, grp = blockIdx.x - 3 * blk;
+  const int64_t b = blocks[blk];
+  const int pen = threadIdx.x, t1 = pen & 7, t2 = pen >> 3;
   const int64_t cell0 = b * CPB;
 #pragma unroll 1
   for (int f = 2 * grp; f < 2 * grp + 2; ++f) {
@@ -77,7 +79,7 @@ k_gen_faces(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ fa
     const float h = bh[b * ND + d], inv_h = 1.0f / h;
     FaceInfo F;
     fill_face_info<ND, BS>(F, bf, 0, h);
-    const int64_t gbase = ((int64_t)blockIdx.x * ND + d) * NSL;
+    const int64_t gbase = ((int64_t)blk * ND + d) * NSL;
     // the three own cells behind the face: c0 on the block face, c1, c2 inwards
     const int bnd = side ? BS - 1 : 0, in = side ? -1 : 1;
     const CellVals c0 = load_cell(P, Dg, N, cell0 + compose<ND, BS>(d, bnd, t1, t2));
@@ -232,7 +234,7 @@ k_sensor_direct(const int32_t* __restrict__ blocks, const BlockFace* __restrict_
         a[side] = acca;
       }
       const float gg = P2 ? (g[1] - g[0]) * ih[d] : (g[1] - g[0]) / h[d], ugg = P2 ? (a[1] + a[0]) * ih[d] : (a[1] + a[0]) / h[d];
-      nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ugg));
+      nu = fmaxf(nu, div_rn_inrange(1e-7f + fabsf(gg), 1e-7f + ugg));   // both operands in [1e-7, ~1e9]: the in-range sequence (physics.cuh)
       stride *= BS;
     }
     D[cell0 + l] = nu;
@@ -286,7 +288,7 @@ k_reg_sensor8(const int32_t* __restrict__ blocks, const BlockFace* __restrict__ 
       const float fh = sp[s + ss] - pc, fl = pc - sp[s - ss];
       const float gg = P2 ? (fh - fl) * ih[d] : (fh - fl) / h[d];
       const float ug = P2 ? (fabsf(fh) + fabsf(fl)) * ih[d] : (fabsf(fh) + fabsf(fl)) / h[d];
-      nu = fmaxf(nu, (1e-7f + fabsf(gg)) / (1e-7f + ug));
+      nu = fmaxf(nu, div_rn_inrange(1e-7f + fabsf(gg), 1e-7f + ug));   // both operands in [1e-7, ~1e9]: the in-range sequence (physics.cuh)
       ss *= PD;
     }
     D[cell0 + l] = nu;
@@ -321,11 +323,11 @@ int general_faces(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n,
                   const float* P, const float* S, double* GF, float* GC, cudaStream_t st) {
   if (n == 0) return IBX_OK;
   if (finer) {
-    if (flux_kind == 0) k_gen_faces<0, true><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
-    else k_gen_faces<1, true><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    if (flux_kind == 0) k_gen_faces<0, true><<<3 * n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    else k_gen_faces<1, true><<<3 * n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
   } else {
-    if (flux_kind == 0) k_gen_faces<0, false><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
-    else k_gen_faces<1, false><<<n, 3 * FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    if (flux_kind == 0) k_gen_faces<0, false><<<3 * n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
+    else k_gen_faces<1, false><<<3 * n, FACE, 0, st>>>(blocks, D.d_block_faces, D.d_block_h, D.ncells, f, P, S, GF, GC);
   }
   LAUNCH_CHECK();
   return IBX_OK;
