@@ -71,3 +71,64 @@ def test_rans_ghost_update_against_oracle(get_case, ib, oracle):
     changed = np.flatnonzero(qRo != qR0)
     assert len(changed) > 1000 and np.array_equal(np.flatnonzero(got != qR0), changed)
     assert np.abs(got - qRo).max() < 2e-6 * np.abs(qRo).max()      # interpolation weights: float32 SVD vs double Jacobi
+
+
+def test_point_implicit_on_the_rans_residual_vs_oracle(get_case, ib, oracle):
+    """C5 "with point_implicit smoothing": linearize (Hutchinson block diagonal, nv = 6: mean flow + transported R) and two
+    preconditioned projection sweeps of `solve` (src/point_implicit.jl:184-329) on the RANS residual, device next to
+    oracle/point_implicit.py with the same counter-based probes.  Unknowns scaled to O(1) (Float32 finite differences)."""
+    from oracle import point_implicit as opi
+    c = get_case("sphere3d_stl", 100_000, upload=True)
+    E, cfd = oracle.euler, oracle.cfd
+    fl, ofl = ib.Fluid(mu_ref=2e-2), cfd.Fluid(mu_ref=F32(2e-2))
+    od = c.odom
+    N, nv = len(od.centers), 6
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(od.centers))
+    qR0 = (Q0[:, 0] * F32(3e-2) * (1 + F32(0.3) * np.sin(F32(2) * od.centers[:, 0]))).astype(F32)
+    X6 = np.concatenate([Q0, qR0[:, None]], axis=1)
+    scale = np.abs(X6).max(axis=0).astype(F32)
+    X0 = (X6 / scale).astype(F32)
+    S5, S1 = ib.DeviceArray.from_host(np.tile(scale[:5], (N, 1))), float(scale[5])
+    S6 = ib.DeviceArray.from_host(np.tile(scale, (N, 1)))
+    CFL, h = F32(0.4), F32(2e-3)
+    res = E.rans_residual(ofl)
+
+    def f(X):
+        Xh = X * S6
+        Q, qR = ib.DeviceArray(N, 5, False), Xh.col(5)
+        for j in range(5):
+            cj = Xh.col(j)
+            ib._lib.call("ibx_array_set_column", ib.context(), Q.h, j, cj.h)
+        R, RR, cf = ib.DeviceArray(N, 5, False), ib.DeviceArray(N, 1, True), ib.DeviceArray(N, 1, True)
+        ib.residual_rans(c.dom, fl, Q, qR, R, RR, cf)
+        out = ib.DeviceArray(N, 6, False)
+        dt = float(CFL) / cf
+        Rs = R * dt / S5
+        for j in range(5):
+            cj = Rs.col(j)
+            ib._lib.call("ibx_array_set_column", ib.context(), out.h, j, cj.h)
+        r6 = RR * dt / S1
+        ib._lib.call("ibx_array_set_column", ib.context(), out.h, 5, r6.h)
+        return out
+
+    def fo(X):
+        Xh = (X * scale).astype(F32)
+        R, RR, cf = np.zeros((N, 5), F32), np.zeros(N, F32), np.zeros(N, F32)
+        od(res, Xh[:, :5].copy(), Xh[:, 5].copy(), R, RR, cf)
+        dt = CFL / cf
+        return np.concatenate([R * dt[:, None] / scale[:5], (RR * dt / scale[5])[:, None]], axis=1).astype(F32)
+
+    probes = ib.synthetic.probe_signs(np.arange(N), nv, 1, seed=5)
+    X = ib.DeviceArray.from_host(X0)
+    fX, foX = f(X), fo(X0)
+    fs = np.abs(foX).max(axis=0)
+    assert (np.abs(fX.to_host() - foX) / fs).max() < 2e-5
+    lin, b, pre = ib.linearize(f, X, n_hutchinson_samples=1, pre_evaluated_fx=fX, h=h, probes=probes)
+    olin, ob, opre = opi.linearize(fo, X0, 1, foX, h, probes=probes)
+    v = (probes[0].T * F32(0.01)).astype(F32)
+    Av, oAv = lin(ib.DeviceArray.from_host(v)).to_host(), olin(v)
+    assert np.abs(Av - oAv).max() < 2e-2 * np.abs(oAv).max()
+    dx, ratio = ib.solve(lin, b, pre, n_iter=2, rtol=1e-6)
+    odx, oratio = opi.solve(olin, ob, opre, n_iter=2, rtol=F32(1e-6))
+    assert np.isfinite(dx.to_host()).all() and float(ratio) < 1.0
+    assert abs(float(ratio) - float(oratio)) < 5e-2 * max(float(oratio), 1e-3), (ratio, oratio)
