@@ -506,9 +506,12 @@ int ibx_euler_step_host_begin(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int 
   CU(cudaMemcpyAsync(Q.p, Q_host, (size_t)N * nv * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
   CU(cudaEventRecord(S.up, c->h2d_stream));
   CU(cudaStreamWaitEvent(c->stream, S.up, 0));
+  // a failure below must not leave the upload in flight behind a slot the caller believes idle (the host buffer is only
+  // borrowed until the matching _end): drain the copy stream before reporting
+  auto bail = [&](int code) { cudaStreamSynchronize(c->h2d_stream); return code; };
   for (int k = 0; k < nbc; ++k)
-    if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, S.Q))) return rc;
-  if ((rc = ibx_residual_euler(c, d, f, flux_kind, S.Q, S.R, S.cfl))) return rc;
+    if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, S.Q))) return bail(rc);
+  if ((rc = ibx_residual_euler(c, d, f, flux_kind, S.Q, S.R, S.cfl))) return bail(rc);
   CU(cudaEventRecord(S.done, c->stream));
   CU(cudaStreamWaitEvent(c->d2h_stream, S.done, 0));
   CU(cudaMemcpyAsync(R_host, R.p, (size_t)N * nv * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));

@@ -1,13 +1,14 @@
 """C3 (BASELINE.json configs[2]): transonic RAE2822 Euler with immersed-boundary ghost cells, marched with local time
 steps through the drop-in boundary (`ibx_euler_step_host`: host state in, residual + CFL term out) next to the oracle
 doing the same march, then lift / drag from the surface pressure integral (Surface + pressure_coefficient +
-surface_integral).  north_star tolerance: lift and drag coefficients within 1e-4.
+surface_integral).  Tolerances asserted below: state within 5e-4 of its per-variable scale, lift and drag coefficients
+within 1e-4 (the north-star figure for Cl / Cd).
 
 The reference ships no Euler residual and no time integrator, so there is no converged reference polar
-to compare with; the canonical residual of SURVEY.md A.10 marched explicitly from an impulsive start develops a
-vacuum at the thin trailing edge after ~28 steps in the ORACLE as well.  The comparison is therefore made on the
-transient after 10 steps, where both paths have processed the same 10 ghost updates + residuals (at 20 steps the
-developing instability already amplifies the 2e-6 difference of the ghost-interpolation weights to ~1e-4)."""
+to compare with; the canonical residual of SURVEY.md A.10 marched from an impulsive start loses its ghost-cell values
+next to the thin trailing edge after ~28 steps in the ORACLE as well (DESIGN.md section 7 localises it).  The comparison
+is therefore made on the transient after 20 steps, where both paths have processed the same 20 ghost updates +
+residuals; the 2e-6 difference of the ghost-interpolation weights is amplified to ~1e-4 of the state scale by then."""
 import numpy as np
 import pytest
 
