@@ -179,7 +179,8 @@ def cpu_reference(level, radius, steps, warmup, stl=None):
         cmd = [sys.executable, os.path.join(ROOT, "tools", "dump_cpu_tables.py"), tmp, str(level), str(radius), str(400_000)]
         if stl is not None:
             cmd += ["stl", str(stl)]
-        subprocess.run(cmd, check=True, cwd=ROOT)
+        # torchrun exports OMP_NUM_THREADS=1: the (untimed) builder process gets all cores back
+        subprocess.run(cmd, check=True, cwd=ROOT, env=dict(os.environ, OMP_NUM_THREADS=str(cores)))
         ref, Q, meta = cpu_ref.CpuRef.from_dump(tmp)
         n, nparts = meta["ncells"], len(meta["parts"])
         fl = ocfd.Fluid()

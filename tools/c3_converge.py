@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--mach", type=float, default=0.73)
     ap.add_argument("--alpha", type=float, default=2.31)
     ap.add_argument("--threads", type=int, default=4)
+    ap.add_argument("--glr", type=float, default=1.5, help="ghost_layer_ratio of Domain (src/ImmersedBoundary.jl:536)")
     ap.add_argument("--moving-interior", action="store_true", help="initialise the cells inside the body with the free stream too")
     args = ap.parse_args()
     import immersedboundary_jl_b200 as ib
@@ -55,7 +56,7 @@ def main():
     feat = M.DistanceField(M.feature_regions(stl, radius=0.05))
     msh = M.Mesh(np.array([-25, -25], F32), np.array([50, 50], F32), ("wall", stl, F32(1e-2)), refinement_regions=[(feat, F32(5e-3))])
     fams = [("farfield", [(0, False), (0, True), (1, False), (1, True)])]
-    dom = ib.Domain(msh, max_partition_size=10_000, hypercube_families=fams, upload=False)
+    dom = ib.Domain(msh, max_partition_size=10_000, hypercube_families=fams, upload=False, ghost_layer_ratio=F32(args.glr))
     ref = cpu_ref.CpuRef.from_builder(dom)
     N = len(dom)
     fl = cfd.Fluid()
