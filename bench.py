@@ -300,11 +300,12 @@ def run_ours(args):
 
     def step():
         if world > 1:
-            dom.halo_exchange(Q)
-        ib.ghost_update_euler(dom, fluid, Q, bcs)
-        if world > 1:
-            dom.halo_begin(Q)      # completed inside residual_euler, behind the conversion of the owned rows
-        ib.residual_euler(dom, fluid, Q, R, cfl)
+            # exchange -> ghost update -> exchange on the halo stream, hidden behind the residual of the blocks that read
+            # neither a ghost nor a halo cell (ibx_step_euler_sharded)
+            ib.step_euler_sharded(dom, fluid, bcs, Q, R, cfl)
+        else:
+            ib.ghost_update_euler(dom, fluid, Q, bcs)
+            ib.residual_euler(dom, fluid, Q, R, cfl)
 
     def barrier():
         ib.synchronize()
@@ -346,6 +347,8 @@ def run_ours(args):
         ib._lib.call("ibx_halo_sizes", dom._h, world, ib._lib.ptr(sc), ib._lib.ptr(rc_))
 
         def timed(fn, reps=20):
+            for _ in range(2):      # untimed: the first whole-domain call after the phased steps grows a scratch buffer
+                fn()
             barrier()
             ib._lib.call("ibx_timer_start", ctx)
             for _ in range(reps):
@@ -361,11 +364,15 @@ def run_ours(args):
         vol = torch.tensor([float(sc.sum()), float(rc_.sum()), float((sc > 0).sum())], device="cuda")
         vmax = vol.clone()
         dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
-        halo = {"exchanges_per_step": 2, "collective": "grouped ncclSend/ncclRecv (pack kernel -> NCCL -> unpack kernel)",
+        ne, nl = C.c_int64(), C.c_int64()
+        ib._lib.call("ibx_shard_phase_info", dom._h, C.byref(ne), C.byref(nl))
+        halo = {"exchanges_per_step": 2, "owned_blocks_early_phase_rank0": ne.value, "owned_blocks_late_phase_rank0": nl.value, "collective": "grouped ncclSend/ncclRecv (pack kernel -> NCCL -> unpack kernel)",
                 "rows_sent_max_rank": int(vmax[0].item()), "rows_received_max_rank": int(vmax[1].item()),
                 "bytes_sent_per_exchange_max_rank": int(vmax[0].item()) * 20, "peers_max_rank": int(vmax[2].item()),
                 "ms_exchange_alone": ms_x, "ms_ghost_update_alone": ms_g, "ms_residual_alone": ms_r,
                 "ms_step": ms_step, "ms_exposed_communication": ms_step - ms_g - ms_r,
+                "overlap": "ibx_step_euler_sharded: exchange 1 + ghost update + exchange 2 on the high-priority halo stream under the residual "
+                           "of the blocks that read neither a ghost nor a halo cell",
                 "coupled_families": sorted(dom.shard_info.get("coupled_families", ())),
                 "limiter": "latency of the two exchanges (3 dependent launches + NCCL each), not bandwidth: "
                            f"{int(vmax[0].item()) * 20 / 1e6:.1f} MB per exchange"}
@@ -477,10 +484,7 @@ def run_ours(args):
 
         def begin(sl):
             ib._lib.call("ibx_array_upload_async", ctx, Qd[sl].h, ib._lib.ptr(Qh[sl]))
-            dom.halo_exchange(Qd[sl])
-            ib.ghost_update_euler(dom, fluid, Qd[sl], bcs)
-            dom.halo_begin(Qd[sl])
-            ib.residual_euler(dom, fluid, Qd[sl], Rd[sl], cd[sl])
+            ib.step_euler_sharded(dom, fluid, bcs, Qd[sl], Rd[sl], cd[sl])
             ib._lib.call("ibx_array_download_async", ctx, Rd[sl].h, ib._lib.ptr(Rh[sl]))
             ib._lib.call("ibx_array_download_async", ctx, cd[sl].h, ib._lib.ptr(ch[sl]))
             ib._lib.call("ibx_download_fence", ctx, sl)

@@ -215,6 +215,18 @@ def ghost_update_euler(dom, fluid, Q, bcs):
         done.append(name)
 
 
+def step_euler_sharded(dom, fluid, bcs, Q, R, cfl, flux="hll"):
+    """One step of a sharded solver loop (``ibx_step_euler_sharded``): halo exchange -> ghost updates of ``bcs`` -> halo
+    exchange on the halo stream, hidden behind the residual of the blocks that read neither a ghost nor a halo cell; then
+    the rest.  Same bits as ``halo_exchange; ghost_update_euler; halo_begin; residual_euler``."""
+    dom.upload()
+    specs = (_lib.BCSpec * max(len(bcs), 1))(*[bc.spec(dom.boundary_index[name]) for name, bc in bcs])
+    coupled = (getattr(dom, "shard_info", None) or {}).get("coupled_families") or ()
+    order = [name for name, _ in bcs]
+    between = any((order[i], order[j]) in coupled for j in range(len(order)) for i in range(j))
+    call("ibx_step_euler_sharded", context(), dom._h, fluid.c, 0 if flux == "hll" else 1, len(bcs), specs, int(between), Q.h, R.h, cfl.h)
+
+
 def residual_advection(dom, u, Cvel, ud, spec):
     """Linear-advection residual of ``test/advection.jl:67-83`` + CFL denominator, whole domain."""
     dom.upload()

@@ -144,7 +144,13 @@ int ibx_comm_finalize(ibx_ctx* c) {
 // Post the halo exchange of array `a` (rows = n_owned + n_halo of the rank-local domain): pack the rows every
 // peer needs on the comm stream, grouped ncclSend/ncclRecv, unpack into the halo rows.  Compute issued on the
 // compute stream after ibx_halo_begin overlaps with the transfer; ibx_halo_end makes the compute stream wait.
-int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
+int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) { return ibx::halo_begin_impl(c, d, ah, true); }
+
+}  // extern "C"
+
+// wait_compute = false: the data to send was produced on the halo stream itself (the ghost update of the overlapped
+// sharded step), so the exchange does not wait for what the compute stream is doing
+int ibx::halo_begin_impl(ibx_ctx* c, const ibx_domain* d, ibx_array ah, bool wait_compute) {
   CHECK_CTX(c);
   GET_DOM(D, d);
   if (!D.shard.active) return fail(IBX_ERR_STATE, "ibx_halo_begin: domain is not a rank-local shard (ibx_domain_shard)");
@@ -154,8 +160,10 @@ int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
   if (A.rows != S.n_owned + S.n_halo) return fail(IBX_ERR_ARG, "ibx_halo_begin: array must have n_owned + n_halo rows");
   int cols = (int)A.cols;
   // the comm stream must see everything the compute stream wrote into `a` so far
-  CU(cudaEventRecord(c->ev_ready, c->stream));
-  CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+  if (wait_compute) {
+    CU(cudaEventRecord(c->ev_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+  }
   for (int peer = 0; peer < S.nranks; ++peer) {
     int64_t ns = (int64_t)S.send_local[peer].size(), nr = (int64_t)S.recv_local[peer].size();
     int64_t need = std::max(ns, nr) * cols;
@@ -233,6 +241,8 @@ int ibx_halo_begin(ibx_ctx* c, const ibx_domain* d, ibx_array ah) {
   c->halo_pending = ah;
   return IBX_OK;
 }
+
+extern "C" {
 
 int ibx_halo_end(ibx_ctx* c, const ibx_domain* d, ibx_array a) {
   CHECK_CTX(c);

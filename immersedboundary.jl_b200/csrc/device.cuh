@@ -68,6 +68,8 @@ int general_faces(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n,
                   const float* P, const float* S, double* GF, float* GC, cudaStream_t st);
 int sensor_direct(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* p, float* S);
 int sensor_regular(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, const float* p, float* S);
+// halo exchange with / without waiting for the compute stream first (comm.cu)
+int halo_begin_impl(ibx_ctx* c, const ibx_domain* d, ibx_array a, bool wait_compute);
 // pencil-marching flux pass (march.cu)
 bool march_supported(const ibx_domain& D);
 int march_flux(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, int n, int hyb, ibx_fluid f, int flux_kind, const float* P,

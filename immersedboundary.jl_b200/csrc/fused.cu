@@ -18,6 +18,8 @@ using namespace ibx;
 using namespace ibxk;
 
 namespace ibx {
+int residual_euler_phase(ibx_ctx* c, const ibx_domain& D, int phase, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,
+                         float* R, float* cfl);
 bool tile_supported(const ibx_domain& D);
 int residual_euler_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,
                          float* R, float* cfl);
@@ -411,8 +413,8 @@ int ibx_residual_advection(ibx_ctx* c, const ibx_domain* d, ibx_array uh, ibx_ar
   return IBX_OK;
 }
 
-int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow,
-                           ibx_array Qh) {
+static int ghost_update_on(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow,
+                           ibx_array Qh, cudaStream_t st) {
   CHECK_CTX(c);
   GET_DOM(D, d);
   if (b < 0 || b >= (int)D.boundaries.size()) return fail(IBX_ERR_ARG, "ibx_ghost_update_euler: boundary index out of range");
@@ -442,19 +444,86 @@ int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, 
   for (auto& B : D.boundaries[b].parts) {
     int64_t G = (int64_t)B.ghost.size();
     int g = grid_for(G, 128, c->sm_count, 16);
-    if (D.nd == 2) k_ghost_stage<2><<<g, 128, 0, c->stream>>>(f, bc, Q.p, N, B.d_ptr, B.d_idx_global, B.d_w, B.d_normals, B.d_eta, stage + off * nv, G);
-    else k_ghost_stage<3><<<g, 128, 0, c->stream>>>(f, bc, Q.p, N, B.d_ptr, B.d_idx_global, B.d_w, B.d_normals, B.d_eta, stage + off * nv, G);
+    if (D.nd == 2) k_ghost_stage<2><<<g, 128, 0, st>>>(f, bc, Q.p, N, B.d_ptr, B.d_idx_global, B.d_w, B.d_normals, B.d_eta, stage + off * nv, G);
+    else k_ghost_stage<3><<<g, 128, 0, st>>>(f, bc, Q.p, N, B.d_ptr, B.d_idx_global, B.d_w, B.d_normals, B.d_eta, stage + off * nv, G);
     LAUNCH_CHECK();
     off += G;
   }
   off = 0;
   for (auto& B : D.boundaries[b].parts) {
     int64_t G = (int64_t)B.ghost.size();
-    k_ghost_commit<<<grid_for(G * nv, TB, c->sm_count, 16), TB, 0, c->stream>>>(stage + off * nv, B.d_ghost, Q.p, N, G, nv);
+    k_ghost_commit<<<grid_for(G * nv, TB, c->sm_count, 16), TB, 0, st>>>(stage + off * nv, B.d_ghost, Q.p, N, G, nv);
     LAUNCH_CHECK();
     off += G;
   }
   return IBX_OK;
+}
+
+int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, const float* Pinf, int n_pinf, int normal_flow,
+                           ibx_array Qh) {
+  if (!c) return fail(IBX_ERR_ARG, "ibx_ghost_update_euler: null context");
+  return ghost_update_on(c, d, b, f, Pinf, n_pinf, normal_flow, Qh, c->stream);
+}
+
+// One step of the sharded solver loop with the communication hidden behind compute ("launch interior cells
+// first, boundary cells after halo_end"):
+//   halo stream (highest priority):  exchange(Q) -> ghost updates of the owned ghosts -> exchange(Q)
+//   compute stream:                  phase 0 (blocks that read neither a ghost nor a halo cell) ... wait ... phase 1 (the rest)
+// Results are those of `halo(Q); ghost updates; halo(Q); ibx_residual_euler` bit for bit (tools/mgpu_check.py).
+int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                           int exchange_between_families, ibx_array Qh, ibx_array Rh, ibx_array cflh) {
+  CHECK_CTX(c);
+  GET_DOM(D, d);
+  int rc;
+  if (!D.shard.active) return fail(IBX_ERR_STATE, "ibx_step_euler_sharded: domain is not a rank-local shard (ibx_domain_shard)");
+  if (flux_kind != 0 && flux_kind != 1) return fail(IBX_ERR_ARG, "ibx_step_euler_sharded: flux_kind must be 0 (HLL) or 1 (sensor-Rusanov)");
+  const bool overlap = D.phased && march_supported(D) && c->opt_path == 0 && D.shard.nranks > 1;
+  if (!overlap) {   // same sequence without the phase split (other block sizes / paths, one rank)
+    if (D.shard.nranks > 1) {
+      if ((rc = ibx_halo_begin(c, d, Qh))) return rc;
+      if ((rc = ibx_halo_end(c, d, Qh))) return rc;
+    }
+    for (int k = 0; k < nbc; ++k) {
+      if (k > 0 && exchange_between_families && D.shard.nranks > 1) {
+        if ((rc = ibx_halo_begin(c, d, Qh))) return rc;
+        if ((rc = ibx_halo_end(c, d, Qh))) return rc;
+      }
+      if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, Qh))) return rc;
+    }
+    if (D.shard.nranks > 1 && (rc = ibx_halo_begin(c, d, Qh))) return rc;
+    return ibx_residual_euler(c, d, f, flux_kind, Qh, Rh, cflh);
+  }
+  GET_ARR(Q, Qh);
+  GET_ARR(R, Rh);
+  GET_ARR(CF, cflh);
+  const int nv = D.nd + 2;
+  const int64_t N = D.ncells;
+  SHAPE(Q.rows == N && Q.cols == nv && R.rows == N && R.cols == nv && CF.rows == N && CF.cols == 1,
+        "Q, R must be ncells x (nd + 2); cfl ncells x 1");
+  // one scratch allocation for both phases and the ghost staging (no reallocation while kernels are in flight)
+  int64_t Gmax = 0;
+  for (int k = 0; k < nbc; ++k) {
+    if (bcs[k].boundary < 0 || bcs[k].boundary >= (int)D.boundaries.size())
+      return fail(IBX_ERR_ARG, "ibx_step_euler_sharded: boundary index out of range");
+    int64_t G = 0;
+    for (auto& B : D.boundaries[bcs[k].boundary].parts) G += (int64_t)B.ghost.size();
+    Gmax = std::max(Gmax, G);
+  }
+  float* scratch = ensure_scratch(c, N * (nv + 1) + Gmax * nv);
+  if (!scratch) return fail(IBX_ERR_CUDA, "ibx_step_euler_sharded: out of device memory for the scratch arrays");
+  float* P = scratch;
+  float* S = scratch + N * nv;
+  if ((rc = halo_begin_impl(c, d, Qh, true))) return rc;                           // exchange 1 (waits for the writers of Q)
+  if ((rc = residual_euler_phase(c, D, 0, f, flux_kind, Q.p, P, S, R.p, CF.p))) return rc;   // phase 0 under it
+  for (int k = 0; k < nbc; ++k) {                                                    // ghost updates behind exchange 1, same stream
+    // a ghost of this family may read, on another rank, a ghost of a family applied above (Domain.shard reports it)
+    if (k > 0 && exchange_between_families && (rc = halo_begin_impl(c, d, Qh, false))) return rc;
+    if ((rc = ghost_update_on(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, Qh, c->comm_stream))) return rc;
+  }
+  if ((rc = halo_begin_impl(c, d, Qh, false))) return rc;                          // exchange 2 behind them
+  CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  c->halo_pending = 0;
+  return residual_euler_phase(c, D, 1, f, flux_kind, Q.p, P, S, R.p, CF.p);
 }
 
 static int e2e_slot_prepare(ibx_ctx* c, ibx_ctx::E2ESlot& S, int64_t N, int nv) {

@@ -218,6 +218,16 @@ struct ibx_domain {
   int32_t *d_blk_all_plain = nullptr, *d_blk_all_finer = nullptr, *d_blk_own_plain = nullptr, *d_blk_own_finer = nullptr;
   int32_t *d_blk_own_regular = nullptr, *d_blk_all_regular = nullptr;  // blocks whose 2*nd neighbours are all same-level blocks (lean kernels)
   int n_all_plain = 0, n_all_finer = 0, n_own_plain = 0, n_own_finer = 0, n_own_regular = 0, n_all_regular = 0;
+  // Shards: block lists of the two phases of the overlapped step (ibx_step_euler_sharded).  Phase 0 ("early") holds the
+  // work that depends neither on a ghost cell nor on a halo cell -- flux blocks whose two rings of face neighbours are
+  // owned and ghost-free, the sensor blocks (one ring) and primitive blocks (two rings) they read -- and runs while the
+  // first exchange, the ghost update and the second exchange are in flight; phase 1 ("late") is everything else.
+  struct PhaseLists {
+    enum { PRIM = 0, S_REG, S_PLAIN, S_FINER, F_REG, F_PLAIN, F_FINER, NLISTS };
+    int32_t* d[NLISTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n[NLISTS] = {0, 0, 0, 0, 0, 0, 0};
+  } phase[2];
+  bool phased = false;
   bool all_pow2 = false;                 // every cell width is a power of two (exact fast paths, physics.cuh)
   ibx::Shard shard;
   ~ibx_domain();

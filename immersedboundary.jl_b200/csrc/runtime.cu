@@ -39,6 +39,9 @@ static void free_tables(ibx_domain& D) {
     for (auto& B : F.parts) { fr(B.d_ghost); fr(B.d_ptr); fr(B.d_idx_global); fr(B.d_image_domain); fr(B.d_idx); fr(B.d_w); fr(B.d_normals); fr(B.d_eta); }
   for (auto& S : D.surfaces) fr(S.d_areas);
   fr(D.d_block_faces); fr(D.d_block_h);
+  for (auto& L : D.phase)
+    for (auto& q : L.d) fr(q);
+  D.phased = false;
   fr(D.d_blk_all_plain); fr(D.d_blk_all_finer); fr(D.d_blk_own_plain); fr(D.d_blk_own_finer); fr(D.d_blk_own_regular); fr(D.d_blk_all_regular);
   for (auto& p : D.shard.d_send) fr(p);
   for (auto& p : D.shard.d_recv) fr(p);
@@ -88,7 +91,13 @@ int ibx_init(int device, ibx_ctx** out) {
   // a failure below must not leak the half-built context: ibx_finalize releases whatever exists
   auto setup = [&]() -> int {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    {
+      // halo exchange, and the ghost update of the overlapped sharded step: highest priority, so that their short kernels
+      // get SM slots while the long flux kernels of the compute stream are resident
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    }
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     CU(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
@@ -461,8 +470,77 @@ int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
     if ((rc = upload_vec(c, af, &D.d_blk_all_finer))) return rc;
     if ((rc = upload_vec(c, op, &D.d_blk_own_plain))) return rc;
     if ((rc = upload_vec(c, of, &D.d_blk_own_finer))) return rc;
+    if (D.shard.active && D.shard.nranks > 1) {
+      // ---- phase lists of the overlapped step.  final0: owned block without ghost cells (its state is final when the step
+      // starts); E = blocks whose two rings of face neighbours are final0.
+      using PL = ibx_domain::PhaseLists;
+      std::vector<uint8_t> final0(nblk, 0), ok1(nblk, 0), inE(nblk, 0), inS(nblk, 0), inP(nblk, 0);
+      for (int64_t b = 0; b < nown; ++b) final0[b] = 1;
+      for (auto& F : D.boundaries)
+        for (auto& B : F.parts)
+          for (int32_t g : B.ghost) final0[(int64_t)g / cpb] = 0;
+      auto for_nbrs = [&](int64_t b, auto&& fn) {
+        for (int f = 0; f < 2 * nd; ++f) {
+          const BlockFace& bf = D.block_faces[(size_t)b * 2 * nd + f];
+          const int cnt = bf.kind == 3 ? (1 << (nd - 1)) : (bf.kind == 1 || bf.kind == 2 ? 1 : 0);
+          for (int q = 0; q < cnt; ++q)
+            if (bf.nb[q] >= 0 && bf.nb[q] < nblk) fn((int64_t)bf.nb[q]);
+        }
+      };
+      for (int64_t b = 0; b < nown; ++b) {
+        bool ok = final0[b];
+        for_nbrs(b, [&](int64_t n) { ok = ok && final0[n]; });
+        ok1[b] = ok;
+      }
+      for (int64_t b = 0; b < nown; ++b) {
+        bool ok = ok1[b];
+        for_nbrs(b, [&](int64_t n) { ok = ok && ok1[n]; });
+        inE[b] = ok;
+      }
+      for (int64_t b = 0; b < nown; ++b)
+        if (inE[b]) {
+          inS[b] = 1;
+          for_nbrs(b, [&](int64_t n) { inS[n] = 1; });
+        }
+      for (int64_t b = 0; b < nblk; ++b)
+        if (inS[b]) {
+          inP[b] = 1;
+          for_nbrs(b, [&](int64_t n) { inP[n] = 1; });
+        }
+      std::vector<int32_t> L[2][PL::NLISTS];
+      for (int64_t b = 0; b < nblk; ++b) {
+        bool finer = false, regular = true;
+        for (int f = 0; f < 2 * nd; ++f) {
+          finer |= D.block_faces[(size_t)b * 2 * nd + f].kind == 3;
+          regular &= D.block_faces[(size_t)b * 2 * nd + f].kind == 1;
+        }
+        const int cls = regular ? 0 : (finer ? 2 : 1);
+        L[inP[b] ? 0 : 1][PL::PRIM].push_back((int32_t)b);
+        L[inS[b] ? 0 : 1][PL::S_REG + cls].push_back((int32_t)b);
+        if (b < nown) L[inE[b] ? 0 : 1][PL::F_REG + cls].push_back((int32_t)b);
+      }
+      for (int ph = 0; ph < 2; ++ph)
+        for (int k = 0; k < PL::NLISTS; ++k) {
+          D.phase[ph].n[k] = (int)L[ph][k].size();
+          if ((rc = upload_vec(c, L[ph][k], &D.phase[ph].d[k]))) return rc;
+        }
+      D.phased = true;
+    }
   }
   CU(cudaStreamSynchronize(c->stream));
+  return IBX_OK;
+}
+
+int ibx_shard_phase_info(const ibx_domain* d, int64_t* n_flux_early, int64_t* n_flux_late) {
+  ibx_domain* Dp = find_domain(d);
+  if (!Dp) return fail(IBX_ERR_ARG, "ibx_shard_phase_info: unknown domain handle");
+  if (!Dp->uploaded) return fail(IBX_ERR_STATE, "ibx_shard_phase_info: domain tables not uploaded (ibx_domain_upload)");
+  using PL = ibx_domain::PhaseLists;
+  int64_t n[2] = {0, 0};
+  for (int ph = 0; ph < 2; ++ph)
+    for (int k = PL::F_REG; k <= PL::F_FINER; ++k) n[ph] += Dp->phase[ph].n[k];
+  *n_flux_early = Dp->phased ? n[0] : 0;
+  *n_flux_late = Dp->phased ? n[1] : 0;
   return IBX_OK;
 }
 

@@ -925,13 +925,20 @@ int launch_tile_sensor(ibx_ctx* c, const ibx_domain& D, const int32_t* blocks, i
 }
 
 // general-face pass of the irregular blocks (MODE 1) followed by the marching kernel on all owned blocks
+// the owned blocks to process, by class: regular / irregular without / with finer neighbours
+struct FluxLists {
+  const int32_t *regular, *plain, *finer;
+  int n_regular, n_plain, n_finer;
+};
+
 template <int ND, int BS>
-int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* P, const float* S, float* R, float* cfl) {
+int run_march(ibx_ctx* c, const ibx_domain& D, const FluxLists& FL, ibx_fluid f, int flux_kind, const float* P, const float* S, float* R,
+              float* cfl) {
   using CP = HybCfg<ND, BS, false>;
   using CF = HybCfg<ND, BS, true>;
   constexpr int NV = CP::NV;
   int rc;
-  const int64_t sl_p = (int64_t)D.n_own_plain * ND * (4 * CP::FACE + CP::NX), sl_f = (int64_t)D.n_own_finer * ND * (4 * CF::FACE + CF::NX);
+  const int64_t sl_p = (int64_t)FL.n_plain * ND * (4 * CP::FACE + CP::NX), sl_f = (int64_t)FL.n_finer * ND * (4 * CF::FACE + CF::NX);
   const int64_t need = (sl_p + sl_f) * (NV * 2 + 1);  // floats: NV doubles + 1 float per slot
   if (need > c->scratch2_cap) {
     if (c->d_scratch2) cudaFree(c->d_scratch2);
@@ -957,20 +964,69 @@ int run_march(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   CU(cudaEventRecord(c->aux_fork, c->stream));
   CU(cudaStreamWaitEvent(sp, c->aux_fork, 0));
   CU(cudaStreamWaitEvent(sf, c->aux_fork, 0));
-  if (D.n_own_plain) {
-    if ((rc = general_faces(c, D, D.d_blk_own_plain, D.n_own_plain, false, f, flux_kind, P, S, GFp, GCp, sp))) return rc;
-    if ((rc = march_flux(c, D, D.d_blk_own_plain, D.n_own_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp, sp))) return rc;
+  if (FL.n_plain) {
+    if ((rc = general_faces(c, D, FL.plain, FL.n_plain, false, f, flux_kind, P, S, GFp, GCp, sp))) return rc;
+    if ((rc = march_flux(c, D, FL.plain, FL.n_plain, 1, f, flux_kind, P, S, R, cfl, GFp, GCp, sp))) return rc;
   }
-  if (D.n_own_finer) {
-    if ((rc = general_faces(c, D, D.d_blk_own_finer, D.n_own_finer, true, f, flux_kind, P, S, GFf, GCf, sf))) return rc;
-    if ((rc = march_flux(c, D, D.d_blk_own_finer, D.n_own_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf, sf))) return rc;
+  if (FL.n_finer) {
+    if ((rc = general_faces(c, D, FL.finer, FL.n_finer, true, f, flux_kind, P, S, GFf, GCf, sf))) return rc;
+    if ((rc = march_flux(c, D, FL.finer, FL.n_finer, 2, f, flux_kind, P, S, R, cfl, GFf, GCf, sf))) return rc;
   }
-  if ((rc = march_flux(c, D, D.d_blk_own_regular, D.n_own_regular, 0, f, flux_kind, P, S, R, cfl, nullptr, nullptr, c->stream))) return rc;
+  if ((rc = march_flux(c, D, FL.regular, FL.n_regular, 0, f, flux_kind, P, S, R, cfl, nullptr, nullptr, c->stream))) return rc;
   CU(cudaEventRecord(c->aux_join[0], sp));
   CU(cudaEventRecord(c->aux_join[1], sf));
   CU(cudaStreamWaitEvent(c->stream, c->aux_join[0], 0));
   CU(cudaStreamWaitEvent(c->stream, c->aux_join[1], 0));
   return IBX_OK;
+}
+
+// Q -> P on the listed 8^3 blocks: one CTA of 128 threads per block, four consecutive cells per thread
+__global__ void __launch_bounds__(128) k_prim_blocks8(ibx_fluid f, const int32_t* __restrict__ blocks, const float* __restrict__ Q,
+                                                       float* __restrict__ P, int64_t n) {
+  const int64_t i = (int64_t)blocks[blockIdx.x] * 512 + 4 * threadIdx.x;
+  float4 q[5], p[5];
+#pragma unroll
+  for (int v = 0; v < 5; ++v) q[v] = *reinterpret_cast<const float4*>(Q + (int64_t)v * n + i);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float qi[5], pi[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) qi[v] = k == 0 ? q[v].x : (k == 1 ? q[v].y : (k == 2 ? q[v].z : q[v].w));
+    s2p<3>(f, qi, pi);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      if (k == 0) p[v].x = pi[v];
+      else if (k == 1) p[v].y = pi[v];
+      else if (k == 2) p[v].z = pi[v];
+      else p[v].w = pi[v];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 5; ++v) *reinterpret_cast<float4*>(P + (int64_t)v * n + i) = p[v];
+}
+
+// one phase of the overlapped sharded step (3-D, 8^3 blocks, marching kernels): primitives, sensors and fluxes of the
+// phase's block lists, on the compute stream
+int run_phase(ibx_ctx* c, const ibx_domain& D, const ibx_domain::PhaseLists& L, ibx_fluid f, int flux_kind, const float* Q, float* P,
+              float* S, float* R, float* cfl) {
+  using PL = ibx_domain::PhaseLists;
+  int rc;
+  if (L.n[PL::PRIM]) {
+    k_prim_blocks8<<<L.n[PL::PRIM], 128, 0, c->stream>>>(f, L.d[PL::PRIM], Q, P, D.ncells);
+    LAUNCH_CHECK();
+  }
+  if (c->opt_sensor == 0) {
+    if (L.n[PL::PRIM]) {   // D == 1 everywhere: filled once per phase for the blocks whose primitives are new (superset of the sensor lists)
+      fill_ones<<<grid_for(D.ncells, 256, c->sm_count, 16), 256, 0, c->stream>>>(S, D.ncells);
+      LAUNCH_CHECK();
+    }
+  } else {
+    if ((rc = sensor_regular(c, D, L.d[PL::S_REG], L.n[PL::S_REG], P, S))) return rc;
+    if ((rc = sensor_direct(c, D, L.d[PL::S_PLAIN], L.n[PL::S_PLAIN], P, S))) return rc;
+    if ((rc = sensor_direct(c, D, L.d[PL::S_FINER], L.n[PL::S_FINER], P, S))) return rc;
+  }
+  const FluxLists FL{L.d[PL::F_REG], L.d[PL::F_PLAIN], L.d[PL::F_FINER], L.n[PL::F_REG], L.n[PL::F_PLAIN], L.n[PL::F_FINER]};
+  return run_march<3, 8>(c, D, FL, f, flux_kind, P, S, R, cfl);
 }
 
 template <int ND, int BS>
@@ -1028,7 +1084,10 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
   // 3-D 8^3 blocks with power-of-two spacings: pencil-marching kernel (march.cu) on every owned block; the general
   // faces of the irregular blocks are computed first (MODE 1) and handed over through a global scratch
   if constexpr (ND == 3 && BS == 8) {
-    if (march) return run_march<ND, BS>(c, D, f, flux_kind, P, S, R, cfl);
+    if (march) {
+      const FluxLists FL{D.d_blk_own_regular, D.d_blk_own_plain, D.d_blk_own_finer, D.n_own_regular, D.n_own_plain, D.n_own_finer};
+      return run_march<ND, BS>(c, D, FL, f, flux_kind, P, S, R, cfl);
+    }
   }
   if (c->opt_arith != 0)
     return fail(IBX_ERR_UNSUPPORTED, "ibx_residual_euler: arithmetic = 1 (fast) exists for the marching kernels only (3-D, block size 8, "
@@ -1050,6 +1109,12 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
 namespace ibx {
 
 bool tile_supported(const ibx_domain& D) { return D.block_size == 8 || D.block_size == 4 || D.block_size == 2; }
+
+// phase 0 / 1 of the overlapped sharded step (see ibx_domain::PhaseLists); P (N x nv) and S (N) are scratch
+int residual_euler_phase(ibx_ctx* c, const ibx_domain& D, int phase, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,
+                         float* R, float* cfl) {
+  return run_phase(c, D, D.phase[phase], f, flux_kind, Q, P, S, R, cfl);
+}
 
 // Euler residual through the tile kernels; P (N x nv) and S (N) are scratch
 int residual_euler_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,

@@ -409,6 +409,17 @@ int ibx_shard_set_send(ibx_domain* local, int peer, int64_t n, const int32_t* gl
 int ibx_halo_begin(ibx_ctx* c, const ibx_domain* local, ibx_array a);
 int ibx_halo_end(ibx_ctx* c, const ibx_domain* local, ibx_array a);
 int ibx_allreduce(ibx_ctx* c, int op /* 0 sum 1 max 2 min */, double* inout, int n);
+/* One step of a sharded solver loop with the communication hidden behind compute: on the halo stream exchange(Q) -> ghost
+ * updates of `bcs` (in order) -> exchange(Q); on the compute stream the residual of the blocks that read neither a ghost
+ * nor a halo cell, then -- after the second exchange -- the rest.  Same results as ibx_halo_begin/_end +
+ * ibx_ghost_update_euler + ibx_halo_begin + ibx_residual_euler, bit for bit.  Falls back to that sequence where the
+ * phase split does not apply (other block sizes / option "path" != 0 / one rank).  exchange_between_families != 0: the halo
+ * rows are also refreshed between consecutive families (needed when a ghost of one family interpolates from a ghost of an
+ * earlier family owned by another rank; the host program detects this when it trades the halo lists). */
+/* owned blocks in the early / late phase of ibx_step_euler_sharded (0, 0 if the phase split does not apply) */
+int ibx_shard_phase_info(const ibx_domain* local, int64_t* n_flux_early, int64_t* n_flux_late);
+int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* local, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                           int exchange_between_families, ibx_array Q, ibx_array R, ibx_array cfl);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,15 @@ def case(label, msh, expect_coupled):
         ib.ghost_update_euler(loc, fl, Ql, bcs)
         loc.halo_begin(Ql)      # completed inside residual_euler (overlapped with compute on the owned rows)
         ib.residual_euler(loc, fl, Ql, Rl, cl)
+    # the same two steps through the overlapped entry point (phase split: exchange + ghost update hidden behind the blocks
+    # that read neither a ghost nor a halo cell)
+    Qf = ib.DeviceArray.from_host(Ql0)
+    Rf, cf2 = ib.DeviceArray(len(loc), 5, False), ib.DeviceArray(len(loc), 1, True)
+    for _ in range(2):
+        ib.step_euler_sharded(loc, fl, bcs, Qf, Rf, cf2)
+    ib.synchronize()
+    okF = (np.array_equal(Rf.to_host()[:n_owned], Rl.to_host()[:n_owned]) and np.array_equal(cf2.to_host()[:n_owned], cl.to_host()[:n_owned])
+           and np.array_equal(Qf.to_host()[:n_owned], Ql.to_host()[:n_owned]))
     own = l2g[:n_owned]
     okR = np.array_equal(Rl.to_host()[:n_owned], Rg.to_host()[own])
     okc = np.array_equal(cl.to_host()[:n_owned], cg.to_host()[own])
@@ -77,8 +86,8 @@ def case(label, msh, expect_coupled):
     dR = np.abs(Rl.to_host()[:n_owned] - Rg.to_host()[own]).max(axis=1)
     coupled = sorted(info.get("coupled_families", ()))
     print(f"[{label}] rank {rank}: owned {n_owned} halo {info['n_halo']} exchanged {len(need)} coupled {coupled} | first exchange {ok0} "
-          f"Q {okQ} R {okR} cfl {okc} (cells with R mismatch {(dR > 0).sum()})", flush=True)
-    ok = ok0 and okR and okc and okQ and (bool(coupled) == expect_coupled)
+          f"Q {okQ} R {okR} cfl {okc} overlapped-step {okF} (cells with R mismatch {(dR > 0).sum()})", flush=True)
+    ok = ok0 and okR and okc and okQ and okF and (bool(coupled) == expect_coupled)
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return t.item() == 1
