@@ -304,8 +304,7 @@ def run_ours(args):
             # neither a ghost nor a halo cell (ibx_step_euler_sharded)
             ib.step_euler_sharded(dom, fluid, bcs, Q, R, cfl)
         else:
-            ib.ghost_update_euler(dom, fluid, Q, bcs)
-            ib.residual_euler(dom, fluid, Q, R, cfl)
+            ib.step_euler(dom, fluid, bcs, Q, R, cfl)   # ghost updates on a second stream under the ghost-free blocks' residual
 
     def barrier():
         ib.synchronize()
@@ -379,6 +378,8 @@ def run_ours(args):
 
     # dominant kernel alone (CUDA events on the library's compute stream) for the roofline entry
     reps = max(3, min(args.steps, 10))
+    for _ in range(2):      # untimed: the first whole-domain call after the phased steps grows a scratch buffer
+        ib.residual_euler(dom, fluid, Q, R, cfl)
     ib._lib.call("ibx_timer_start", ctx)
     for _ in range(reps):
         ib.residual_euler(dom, fluid, Q, R, cfl)

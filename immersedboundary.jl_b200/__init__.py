@@ -15,7 +15,7 @@ from .domain import (Domain, Partition, Boundary, Surface, DeviceArray, Accumula
 from .cfd import (Fluid, FlowBC, state2primitive, primitive2state, speed_of_sound, inviscid_fluxes,  # noqa: F401
                   dynamic_viscosity, heat_conductivity, viscous_fluxes, JST_sensor_3pt, shock_sensor, pressure_coefficient,
                   streamwise_direction, Reynolds_number, adjust_Reynolds,
-                  residual_euler, residual_rans, step_euler_sharded, ghost_update_euler, ghost_update_rans, residual_advection, euler_step_host, euler_step_host_begin,
+                  residual_euler, residual_rans, step_euler, step_euler_sharded, ghost_update_euler, ghost_update_rans, residual_advection, euler_step_host, euler_step_host_begin,
                   euler_step_host_end, pinned_empty)
 from .solver import FAS, Multigrid, PIPreconditioner, hutchinson_trick, Linearization, linearize, proj_along, solve  # noqa: F401
 from .vtk import export_vtk, vtk_grid_mesh, vtk_grid_stl  # noqa: F401

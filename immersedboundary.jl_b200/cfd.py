@@ -215,6 +215,15 @@ def ghost_update_euler(dom, fluid, Q, bcs):
         done.append(name)
 
 
+def step_euler(dom, fluid, bcs, Q, R, cfl, flux="hll"):
+    """One step of a solver loop on a whole domain (``ibx_step_euler``): ghost updates of ``bcs`` then the residual, the ghost
+    update hidden behind the residual of the blocks that do not read a ghost cell.  Same bits as ``ghost_update_euler`` +
+    ``residual_euler``."""
+    dom.upload()
+    specs = (_lib.BCSpec * max(len(bcs), 1))(*[bc.spec(dom.boundary_index[name]) for name, bc in bcs])
+    call("ibx_step_euler", context(), dom._h, fluid.c, 0 if flux == "hll" else 1, len(bcs), specs, Q.h, R.h, cfl.h)
+
+
 def step_euler_sharded(dom, fluid, bcs, Q, R, cfl, flux="hll"):
     """One step of a sharded solver loop (``ibx_step_euler_sharded``): halo exchange -> ghost updates of ``bcs`` -> halo
     exchange on the halo stream, hidden behind the residual of the blocks that read neither a ghost nor a halo cell; then

@@ -465,32 +465,33 @@ int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, 
   return ghost_update_on(c, d, b, f, Pinf, n_pinf, normal_flow, Qh, c->stream);
 }
 
-// One step of the sharded solver loop with the communication hidden behind compute ("launch interior cells
-// first, boundary cells after halo_end"):
-//   halo stream (highest priority):  exchange(Q) -> ghost updates of the owned ghosts -> exchange(Q)
+// One step of the solver loop -- ghost updates of `bcs`, then the residual -- with everything that is not flux work hidden
+// behind compute ("launch interior cells first, boundary cells after halo_end"):
+//   halo stream (highest priority):  [exchange(Q) ->] ghost updates of the owned ghosts [-> exchange(Q)]
 //   compute stream:                  phase 0 (blocks that read neither a ghost nor a halo cell) ... wait ... phase 1 (the rest)
-// Results are those of `halo(Q); ghost updates; halo(Q); ibx_residual_euler` bit for bit (tools/mgpu_check.py).
-int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+// The exchanges exist on rank-local shards only.  Results are those of `[halo(Q);] ghost updates; [halo(Q);] ibx_residual_euler`
+// bit for bit (tools/mgpu_check.py, tests/test_fused_gpu.py).
+static int step_euler_impl(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
                            int exchange_between_families, ibx_array Qh, ibx_array Rh, ibx_array cflh) {
   CHECK_CTX(c);
   GET_DOM(D, d);
   int rc;
-  if (!D.shard.active) return fail(IBX_ERR_STATE, "ibx_step_euler_sharded: domain is not a rank-local shard (ibx_domain_shard)");
-  if (flux_kind != 0 && flux_kind != 1) return fail(IBX_ERR_ARG, "ibx_step_euler_sharded: flux_kind must be 0 (HLL) or 1 (sensor-Rusanov)");
-  const bool overlap = D.phased && march_supported(D) && c->opt_path == 0 && D.shard.nranks > 1;
-  if (!overlap) {   // same sequence without the phase split (other block sizes / paths, one rank)
-    if (D.shard.nranks > 1) {
+  if (flux_kind != 0 && flux_kind != 1) return fail(IBX_ERR_ARG, "ibx_step_euler: flux_kind must be 0 (HLL) or 1 (sensor-Rusanov)");
+  const bool sharded = D.shard.active && D.shard.nranks > 1;
+  const bool overlap = D.phased && march_supported(D) && c->opt_path == 0;
+  if (!overlap) {   // same sequence without the phase split (2-D, other block sizes / paths)
+    if (sharded) {
       if ((rc = ibx_halo_begin(c, d, Qh))) return rc;
       if ((rc = ibx_halo_end(c, d, Qh))) return rc;
     }
     for (int k = 0; k < nbc; ++k) {
-      if (k > 0 && exchange_between_families && D.shard.nranks > 1) {
+      if (k > 0 && exchange_between_families && sharded) {
         if ((rc = ibx_halo_begin(c, d, Qh))) return rc;
         if ((rc = ibx_halo_end(c, d, Qh))) return rc;
       }
       if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, Qh))) return rc;
     }
-    if (D.shard.nranks > 1 && (rc = ibx_halo_begin(c, d, Qh))) return rc;
+    if (sharded && (rc = ibx_halo_begin(c, d, Qh))) return rc;
     return ibx_residual_euler(c, d, f, flux_kind, Qh, Rh, cflh);
   }
   GET_ARR(Q, Qh);
@@ -504,26 +505,53 @@ int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flu
   int64_t Gmax = 0;
   for (int k = 0; k < nbc; ++k) {
     if (bcs[k].boundary < 0 || bcs[k].boundary >= (int)D.boundaries.size())
-      return fail(IBX_ERR_ARG, "ibx_step_euler_sharded: boundary index out of range");
+      return fail(IBX_ERR_ARG, "ibx_step_euler: boundary index out of range");
     int64_t G = 0;
     for (auto& B : D.boundaries[bcs[k].boundary].parts) G += (int64_t)B.ghost.size();
     Gmax = std::max(Gmax, G);
   }
   float* scratch = ensure_scratch(c, N * (nv + 1) + Gmax * nv);
-  if (!scratch) return fail(IBX_ERR_CUDA, "ibx_step_euler_sharded: out of device memory for the scratch arrays");
+  if (!scratch) return fail(IBX_ERR_CUDA, "ibx_step_euler: out of device memory for the scratch arrays");
   float* P = scratch;
   float* S = scratch + N * nv;
-  if ((rc = halo_begin_impl(c, d, Qh, true))) return rc;                           // exchange 1 (waits for the writers of Q)
+  if (c->halo_pending) {   // an exchange posted by the caller: complete it first
+    CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+    c->halo_pending = 0;
+  }
+  if (sharded) {
+    if ((rc = halo_begin_impl(c, d, Qh, true))) return rc;                         // exchange 1 (waits for the writers of Q)
+  } else {
+    CU(cudaEventRecord(c->ev_ready, c->stream));                                     // the ghost update sees the writers of Q
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+  }
   if ((rc = residual_euler_phase(c, D, 0, f, flux_kind, Q.p, P, S, R.p, CF.p))) return rc;   // phase 0 under it
-  for (int k = 0; k < nbc; ++k) {                                                    // ghost updates behind exchange 1, same stream
+  for (int k = 0; k < nbc; ++k) {                                                    // ghost updates on the halo stream
     // a ghost of this family may read, on another rank, a ghost of a family applied above (Domain.shard reports it)
-    if (k > 0 && exchange_between_families && (rc = halo_begin_impl(c, d, Qh, false))) return rc;
+    if (k > 0 && exchange_between_families && sharded && (rc = halo_begin_impl(c, d, Qh, false))) return rc;
     if ((rc = ghost_update_on(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, Qh, c->comm_stream))) return rc;
   }
-  if ((rc = halo_begin_impl(c, d, Qh, false))) return rc;                          // exchange 2 behind them
+  if (sharded) {
+    if ((rc = halo_begin_impl(c, d, Qh, false))) return rc;                        // exchange 2 behind them
+  } else {
+    CU(cudaEventRecord(c->ev_halo, c->comm_stream));
+  }
   CU(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
   c->halo_pending = 0;
   return residual_euler_phase(c, D, 1, f, flux_kind, Q.p, P, S, R.p, CF.p);
+}
+
+int ibx_step_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs, ibx_array Qh, ibx_array Rh,
+                   ibx_array cflh) {
+  return step_euler_impl(c, d, f, flux_kind, nbc, bcs, 0, Qh, Rh, cflh);
+}
+
+int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
+                           int exchange_between_families, ibx_array Qh, ibx_array Rh, ibx_array cflh) {
+  if (c) {
+    ibx_domain* Dp = find_domain(d);
+    if (Dp && !Dp->shard.active) return fail(IBX_ERR_STATE, "ibx_step_euler_sharded: domain is not a rank-local shard (ibx_domain_shard)");
+  }
+  return step_euler_impl(c, d, f, flux_kind, nbc, bcs, exchange_between_families, Qh, Rh, cflh);
 }
 
 static int e2e_slot_prepare(ibx_ctx* c, ibx_ctx::E2ESlot& S, int64_t N, int nv) {
@@ -578,9 +606,7 @@ int ibx_euler_step_host_begin(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int 
   // a failure below must not leave the upload in flight behind a slot the caller believes idle (the host buffer is only
   // borrowed until the matching _end): drain the copy stream before reporting
   auto bail = [&](int code) { cudaStreamSynchronize(c->h2d_stream); return code; };
-  for (int k = 0; k < nbc; ++k)
-    if ((rc = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, S.Q))) return bail(rc);
-  if ((rc = ibx_residual_euler(c, d, f, flux_kind, S.Q, S.R, S.cfl))) return bail(rc);
+  if ((rc = step_euler_impl(c, d, f, flux_kind, nbc, bcs, 0, S.Q, S.R, S.cfl))) return bail(rc);
   CU(cudaEventRecord(S.done, c->stream));
   CU(cudaStreamWaitEvent(c->d2h_stream, S.done, 0));
   CU(cudaMemcpyAsync(R_host, R.p, (size_t)N * nv * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));

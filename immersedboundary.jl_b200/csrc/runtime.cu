@@ -470,8 +470,8 @@ int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
     if ((rc = upload_vec(c, af, &D.d_blk_all_finer))) return rc;
     if ((rc = upload_vec(c, op, &D.d_blk_own_plain))) return rc;
     if ((rc = upload_vec(c, of, &D.d_blk_own_finer))) return rc;
-    if (D.shard.active && D.shard.nranks > 1) {
-      // ---- phase lists of the overlapped step.  final0: owned block without ghost cells (its state is final when the step
+    if (nd == 3 && D.block_size == 8) {
+      // ---- phase lists of the overlapped step (whole domains: only the ghost update is hidden; shards: the exchanges too).  final0: owned block without ghost cells (its state is final when the step
       // starts); E = blocks whose two rings of face neighbours are final0.
       using PL = ibx_domain::PhaseLists;
       std::vector<uint8_t> final0(nblk, 0), ok1(nblk, 0), inE(nblk, 0), inS(nblk, 0), inP(nblk, 0);

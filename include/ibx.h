@@ -375,9 +375,15 @@ int ibx_ghost_update_rans(ibx_ctx* c, const ibx_domain* d, int b, ibx_array Q, i
  * image interpolation of P = state2primitive(Q), BC, eta-blend, primitive2state, written Jacobi-style. */
 int ibx_ghost_update_euler(ibx_ctx* c, const ibx_domain* d, int b, ibx_fluid f, const float* Pinf, int n_pinf,
                            int normal_flow, ibx_array Q);
+typedef struct ibx_bc_spec { int boundary; int normal_flow; int n_pinf; float Pinf[5]; } ibx_bc_spec;
+/* One step of a solver loop on a whole (unsharded) domain: ghost updates of `bcs` in order, then the residual -- with the
+ * ghost update running on a second, high-priority stream under the residual of the blocks that do not read a ghost cell
+ * (3-D, block size 8; elsewhere the plain sequence).  Same bits as ibx_ghost_update_euler x nbc + ibx_residual_euler.
+ * ibx_step_euler_sharded (below) is the same call on a rank-local shard, where the halo exchanges are hidden too. */
+int ibx_step_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs, ibx_array Q,
+                   ibx_array R, ibx_array cfl);
 /* End-to-end convenience for hosts that hold the state in host memory: H2D(Q) -> ghost updates of
  * every boundary in `bcs` order -> residual -> D2H(R, cfl).  Host buffers column-major. */
-typedef struct ibx_bc_spec { int boundary; int normal_flow; int n_pinf; float Pinf[5]; } ibx_bc_spec;
 int ibx_euler_step_host(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
                         const float* Q_host, float* R_host, float* cfl_host);
 /* The same call split in two so that consecutive, independent evaluations (finite-difference JVP probes of

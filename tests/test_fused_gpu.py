@@ -282,3 +282,28 @@ def test_residual_without_sensor_blend(get_case, ib, oracle, name, mps):
         R, cf = ib.DeviceArray(N, nd + 2, False), ib.DeviceArray(N, 1, True)
         ib.residual_euler(c.dom, fl, ib.DeviceArray.from_host(Q0), R, cf)
     assert np.array_equal(R.to_host(), Ro) and np.array_equal(cf.to_host(), co)
+
+
+@pytest.mark.parametrize("name,mps", [("sphere3d", 40_000), ("rae2822", 10_000)])
+def test_overlapped_step_equals_ghost_update_plus_residual(get_case, ib, name, mps):
+    """ibx_step_euler: the ghost update runs on a second stream under the residual of the blocks that do not read a ghost cell
+    (3-D, block size 8; the plain sequence elsewhere).  Same bits as the two calls, also when repeated and in fast mode."""
+    c = get_case(name, mps, upload=True)
+    fl = ib.Fluid()
+    nd = c.dom.ndims
+    N = len(c.dom)
+    bcs = _bcs(ib, fl, nd)
+    Q0 = ib.synthetic.primitive2state_host(ib.synthetic.euler_state(c.dom.cells()[0]))
+    for opts in ({}, {"arithmetic": 1}, {"sensor": 0}):
+        if name == "rae2822" and opts.get("arithmetic"):
+            continue
+        with ib.options(**opts):
+            Qa, Qb = ib.DeviceArray.from_host(Q0), ib.DeviceArray.from_host(Q0)
+            Ra, ca = ib.DeviceArray(N, nd + 2, False), ib.DeviceArray(N, 1, True)
+            Rb, cb = ib.DeviceArray(N, nd + 2, False), ib.DeviceArray(N, 1, True)
+            for _ in range(3):
+                ib.ghost_update_euler(c.dom, fl, Qa, bcs)
+                ib.residual_euler(c.dom, fl, Qa, Ra, ca)
+                ib.step_euler(c.dom, fl, bcs, Qb, Rb, cb)
+            assert np.array_equal(Qa.to_host(), Qb.to_host()), opts
+            assert np.array_equal(Ra.to_host(), Rb.to_host()) and np.array_equal(ca.to_host(), cb.to_host()), opts
