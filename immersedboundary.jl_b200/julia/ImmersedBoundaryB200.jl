@@ -575,4 +575,30 @@ euler_step_host_end(slot::Int) = check(ccall((:ibx_euler_step_host_end, libibx),
 halo_begin!(dom::Domain, a::IBXArray) = check(ccall((:ibx_halo_begin, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), context(), dom.h, a.h))
 halo_end!(dom::Domain, a::IBXArray) = check(ccall((:ibx_halo_end, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), context(), dom.h, a.h))
 
+"""One step of a solver loop: ghost updates of `bcs` in order, then the residual, with the ghost update (and, on a rank-local
+shard, both halo exchanges) hidden behind the residual of the blocks that read neither a ghost nor a halo cell
+(`ibx_step_euler` / `ibx_step_euler_sharded`).  Same bits as `ghost_update_euler!` + `residual_euler!`."""
+function step_euler!(dom::Domain, fluid::Fluid, bcs::Vector{Pair{String, FlowBC}}, Q::IBXArray, R::IBXArray, cfl::IBXArray;
+                     flux_kind::Int = 0, sharded::Bool = false, exchange_between_families::Bool = false)
+    specs = [BCSpec(dom, n, bc) for (n, bc) in bcs]
+    GC.@preserve specs begin
+        if sharded
+            check(ccall((:ibx_step_euler_sharded, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Fluid, Cint, Cint, Ptr{BCSpec}, Cint, Int64, Int64, Int64),
+                        context(), dom.h, fluid, flux_kind, length(specs), specs, exchange_between_families, Q.h, R.h, cfl.h))
+        else
+            check(ccall((:ibx_step_euler, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Fluid, Cint, Cint, Ptr{BCSpec}, Int64, Int64, Int64),
+                        context(), dom.h, fluid, flux_kind, length(specs), specs, Q.h, R.h, cfl.h))
+        end
+    end
+end
+
+"Configuration C5: canonical RANS residual (`ibx_residual_rans`) and the ghost update of the transported variable."
+residual_rans!(dom::Domain, fluid::Fluid, Q::IBXArray, qR::IBXArray, R::IBXArray, RR::IBXArray, cfl::IBXArray;
+               transport::Transport = Transport(), σR::Real = 0.72f0, C₁::Real = 0.0829f0, κ::Real = 0.41f0) =
+    check(ccall((:ibx_residual_rans, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Fluid, Transport, Cfloat, Cfloat, Cfloat, Int64, Int64, Int64, Int64, Int64),
+                context(), dom.h, fluid, transport, σR, C₁, κ, Q.h, qR.h, R.h, RR.h, cfl.h))
+ghost_update_rans!(dom::Domain, name::String, Q::IBXArray, qR::IBXArray, R_bc::Real) =
+    check(ccall((:ibx_ghost_update_rans, libibx), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64, Int64, Cfloat), context(), dom.h,
+                dom.boundary_index[name], Q.h, qR.h, R_bc))
+
 end # module
