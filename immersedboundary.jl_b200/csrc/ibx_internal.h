@@ -228,6 +228,8 @@ struct ibx_domain {
     int n[NLISTS] = {0, 0, 0, 0, 0, 0, 0};
   } phase[2];
   bool phased = false;
+  int32_t *d_blk_noghost = nullptr, *d_blk_ghost = nullptr;   // blocks without / with ghost cells (whole-domain overlapped step)
+  int n_blk_noghost = 0, n_blk_ghost = 0;
   bool all_pow2 = false;                 // every cell width is a power of two (exact fast paths, physics.cuh)
   ibx::Shard shard;
   ~ibx_domain();

@@ -42,6 +42,7 @@ static void free_tables(ibx_domain& D) {
   for (auto& L : D.phase)
     for (auto& q : L.d) fr(q);
   D.phased = false;
+  fr(D.d_blk_noghost); fr(D.d_blk_ghost);
   fr(D.d_blk_all_plain); fr(D.d_blk_all_finer); fr(D.d_blk_own_plain); fr(D.d_blk_own_finer); fr(D.d_blk_own_regular); fr(D.d_blk_all_regular);
   for (auto& p : D.shard.d_send) fr(p);
   for (auto& p : D.shard.d_recv) fr(p);
@@ -518,6 +519,14 @@ int ibx_domain_upload(ibx_ctx* c, ibx_domain* d) {
         L[inP[b] ? 0 : 1][PL::PRIM].push_back((int32_t)b);
         L[inS[b] ? 0 : 1][PL::S_REG + cls].push_back((int32_t)b);
         if (b < nown) L[inE[b] ? 0 : 1][PL::F_REG + cls].push_back((int32_t)b);
+      }
+      {
+        std::vector<int32_t> ng, gh;
+        for (int64_t b = 0; b < nblk; ++b) (final0[b] || b >= nown ? ng : gh).push_back((int32_t)b);
+        D.n_blk_noghost = (int)ng.size();
+        D.n_blk_ghost = (int)gh.size();
+        if ((rc = upload_vec(c, ng, &D.d_blk_noghost))) return rc;
+        if ((rc = upload_vec(c, gh, &D.d_blk_ghost))) return rc;
       }
       for (int ph = 0; ph < 2; ++ph)
         for (int k = 0; k < PL::NLISTS; ++k) {

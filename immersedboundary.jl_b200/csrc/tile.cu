@@ -1030,9 +1030,12 @@ int run_phase(ibx_ctx* c, const ibx_domain& D, const ibx_domain::PhaseLists& L, 
 }
 
 template <int ND, int BS>
-int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S, float* R, float* cfl) {
+int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S, float* R, float* cfl,
+              bool prim_done = false) {
   int64_t N = D.ncells;
-  if (c->halo_pending && D.shard.active && D.shard.n_owned <= N) {
+  if (prim_done) {
+    // P was filled by the caller (ibx_step_euler: block-list conversions around the ghost update)
+  } else if (c->halo_pending && D.shard.active && D.shard.n_owned <= N) {
     // a halo exchange of Q is in flight (ibx_halo_begin without ibx_halo_end): convert the owned rows while it runs,
     // then wait for it and convert the halo rows
     const int64_t no = D.shard.n_owned;   // owned rows come first, then the halo rows
@@ -1109,6 +1112,21 @@ int run_tiles(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const
 namespace ibx {
 
 bool tile_supported(const ibx_domain& D) { return D.block_size == 8 || D.block_size == 4 || D.block_size == 2; }
+
+// whole-domain step (3-D, 8^3 blocks): Q -> P on the ghost-free blocks (`early`) / on the blocks holding ghost cells;
+// then sensors and fluxes of every block with the primitives taken as given
+int prim_blocks(ibx_ctx* c, const ibx_domain& D, bool early, ibx_fluid f, const float* Q, float* P) {
+  const int32_t* list = early ? D.d_blk_noghost : D.d_blk_ghost;
+  const int n = early ? D.n_blk_noghost : D.n_blk_ghost;
+  if (n == 0) return IBX_OK;
+  k_prim_blocks8<<<n, 128, 0, c->stream>>>(f, list, Q, P, D.ncells);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
+int residual_euler_after_prim(ibx_ctx* c, const ibx_domain& D, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S, float* R,
+                              float* cfl) {
+  return run_tiles<3, 8>(c, D, f, flux_kind, Q, P, S, R, cfl, true);
+}
 
 // phase 0 / 1 of the overlapped sharded step (see ibx_domain::PhaseLists); P (N x nv) and S (N) are scratch
 int residual_euler_phase(ibx_ctx* c, const ibx_domain& D, int phase, ibx_fluid f, int flux_kind, const float* Q, float* P, float* S,
