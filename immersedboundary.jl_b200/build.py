@@ -56,7 +56,8 @@ def build(force=False, verbose=False):
                     raise RuntimeError(f"nvcc failed on {src}")
     objs = [os.path.join(OBJ, s + ".o") for s in _sources()]
     if jobs or not os.path.exists(LIB) or force or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
+        # -z defs: an undefined symbol fails the build here instead of at dlopen on the GPU box
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-Xlinker", "-z", "-Xlinker", "defs"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
