@@ -25,16 +25,19 @@ constexpr float EPS32 = 1.1920928955078125e-07f;
 
 struct WA { float sigma_R, C1, kappa; };
 
-// Julia's Float32 ^ Float32 is evaluated in Float64 and rounded once (Base.Math.pow_body), like closures.cu
-__device__ __forceinline__ float pw(float x, float y) { return (float)exp2(log2(fabs((double)x)) * (double)y); }
 __device__ __forceinline__ float ipw(float x, int n) {
   double r = 1.0;
   for (int k = 0; k < n; ++k) r *= (double)x;
   return (float)r;
 }
-__device__ __forceinline__ float viscosity(const ibx_transport& t, float T) {   // src/cfd.jl:71-77
+// src/cfd.jl:71-77.  (T / T_ref) ^ (2/3) as cbrt(x)^2 in Float32 (~2 ulp) instead of Julia's Float64 exp2(log2 x * y): the
+// viscosity is evaluated at every face of every cell (12 times per cell), and the Float64 transcendental pair dominated the
+// kernel; 2e-7 relative on mu is far inside the 1e-5 tolerance of the viscous terms (the pointwise ibx_dynamic_viscosity keeps
+// the exact form).
+__device__ __forceinline__ float viscosity(const ibx_transport& t, float T) {
   T = fmaxf(T, 10.0f);
-  return t.mu_ref * pw(T / t.T_ref, 2.0f / 3) * (t.T_ref + t.S) / (T + t.S);
+  const float cr = cbrtf(T / t.T_ref);
+  return t.mu_ref * (cr * cr) * (t.T_ref + t.S) / (T + t.S);
 }
 __device__ __forceinline__ float conductivity(const ibx_transport& t, float T) {   // src/cfd.jl:84-90
   float k = 0.0f * T;

@@ -28,6 +28,17 @@ struct Nbr {
 
 template <int ND>
 __device__ __forceinline__ void decode(const Topo& T, int64_t cell, int64_t& b, int (&ii)[ND]) {
+  if (T.bs == 8) {   // the usual block size: shifts instead of 64-bit divisions by a run-time value (uniform branch)
+    constexpr int LOG_CPB = 3 * ND;
+    b = cell >> LOG_CPB;
+    int l = (int)(cell & ((1 << LOG_CPB) - 1));
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      ii[d] = l & 7;
+      l >>= 3;
+    }
+    return;
+  }
   b = cell / T.cpb;
   int l = (int)(cell - b * T.cpb);
 #pragma unroll
