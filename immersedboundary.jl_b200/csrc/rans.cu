@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(TB) k_rans_source(Topo T, WA wa, const float* 
   }
 }
 
-__global__ void __launch_bounds__(TB) k_rans_flux(Topo T, ibx_transport tr, const float* __restrict__ Q, const float* __restrict__ qR,
+// latency-bound gathers (about 50 scattered loads per face): occupancy matters more than a few spills -> 128 threads, 6 CTAs / SM
+__global__ void __launch_bounds__(128, 6) k_rans_flux(Topo T, ibx_transport tr, const float* __restrict__ Q, const float* __restrict__ qR,
                                                   const float* __restrict__ W, const float* __restrict__ G, const float* __restrict__ AUX,
                                                   const float* __restrict__ SRC, float* __restrict__ R5, float* __restrict__ RR) {
   const int64_t N = T.ncells;
@@ -249,7 +250,7 @@ int ibx_residual_rans(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, ibx_transpor
   LAUNCH_CHECK();
   k_rans_source<<<g, TB, 0, c->stream>>>(T, wa, Q.p, W, G, AUX, SRC);
   LAUNCH_CHECK();
-  k_rans_flux<<<g, TB, 0, c->stream>>>(T, tr, Q.p, QR.p, W, G, AUX, SRC, R.p, RR.p);
+  k_rans_flux<<<grid_for(N, 128, c->sm_count, 32), 128, 0, c->stream>>>(T, tr, Q.p, QR.p, W, G, AUX, SRC, R.p, RR.p);
   LAUNCH_CHECK();
   return IBX_OK;
 }
