@@ -645,9 +645,10 @@ def run_c5(args):
             dom.halo_exchange(Q)
             dom.halo_exchange(qR)
         ib.ghost_update_euler(dom, fluid, Q, bcs)
+        if world > 1:
+            dom.halo_exchange(Q)      # ghost_update_rans divides by the NEW ghost densities, also at donors owned by other ranks
         ib.ghost_update_rans(dom, Q, qR, rbc)
         if world > 1:
-            dom.halo_exchange(Q)
             dom.halo_exchange(qR)
         ib.residual_rans(dom, fluid, Q, qR, R, RR, cfl)
 

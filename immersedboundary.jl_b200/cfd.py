@@ -193,10 +193,18 @@ def residual_rans(dom, fluid, Q, qR, R, RR, cfl, sigma_R=0.72, C1=0.0829, kappa=
 
 def ghost_update_rans(dom, Q, qR, R_bcs):
     """IB ghost update of the transported Wray-Agarwal variable for ``R_bcs = [(boundary name, R value), ...]`` in order
-    (``ibx_ghost_update_rans``); call after ``ghost_update_euler`` (it uses the ghost densities)."""
+    (``ibx_ghost_update_rans``); call after ``ghost_update_euler`` (it uses the ghost densities).  On a rank-local shard
+    exchange ``Q`` in between: a donor that is a ghost cell of another rank must carry its new density too
+    (``tools/mgpu_check.py`` checks the sequence against the single-domain result)."""
     dom.upload()
+    coupled = (getattr(dom, "shard_info", None) or {}).get("coupled_families")
+    done = []
     for name, val in R_bcs:
+        if coupled and any((e, name) in coupled for e in done):
+            dom.halo_exchange(qR)      # like ghost_update_euler: a ghost of this family reads a ghost of an earlier one on another rank
+            done = []
         call("ibx_ghost_update_rans", context(), dom._h, dom.boundary_index[name], Q.h, qR.h, float(val))
+        done.append(name)
 
 
 def ghost_update_euler(dom, fluid, Q, bcs):

@@ -2,6 +2,8 @@
 (halo exchange over NCCL + ghost update + halo exchange + residual) must reproduce, on every rank's owned cells, the
 single-domain result computed on the same GPU -- bit for bit.
 
+Also checked on every case: the overlapped entry point (ibx_step_euler_sharded) and the C5 RANS step (ibx_residual_rans +
+ibx_ghost_update_rans with two exchanged arrays).
 Cases: `sphere` (body far from the box: the two boundary families do not interact) and `close` (a sphere next to a box
 face: wall ghosts interpolate from farfield ghosts owned by other ranks, so ghost_update_euler has to exchange the halo
 rows between the two families -- ADVICE r1)."""
@@ -79,15 +81,44 @@ def case(label, msh, expect_coupled):
     ib.synchronize()
     okF = (np.array_equal(Rf.to_host()[:n_owned], Rl.to_host()[:n_owned]) and np.array_equal(cf2.to_host()[:n_owned], cl.to_host()[:n_owned])
            and np.array_equal(Qf.to_host()[:n_owned], Ql.to_host()[:n_owned]))
+    # configuration C5 on the same shard: RANS residual + ghost update of the transported variable (two exchanged arrays)
+    nu3 = 4.5e-5
+    rbc = [("wall", 0.0), ("farfield", nu3)]
+    qg0 = (Qg0[:, 0] * F32(nu3) * (1 + F32(0.2) * np.sin(g.cells()[0][:, 0]).astype(F32))).astype(F32)
+    Qg2, qg = ib.DeviceArray.from_host(Qg0), ib.DeviceArray.from_host(qg0)
+    Rg2, RRg, cg2 = ib.DeviceArray(len(g), 5, False), ib.DeviceArray(len(g), 1, True), ib.DeviceArray(len(g), 1, True)
+    ql0 = np.zeros(len(loc), F32)
+    ql0[:n_owned] = qg0[l2g[:n_owned]]
+    Ql2, ql = ib.DeviceArray.from_host(Ql0), ib.DeviceArray.from_host(ql0)
+    Rl2, RRl, cl2 = ib.DeviceArray(len(loc), 5, False), ib.DeviceArray(len(loc), 1, True), ib.DeviceArray(len(loc), 1, True)
+    for _ in range(2):
+        ib.ghost_update_euler(g, fl, Qg2, bcs)
+        ib.ghost_update_rans(g, Qg2, qg, rbc)
+        ib.residual_rans(g, fl, Qg2, qg, Rg2, RRg, cg2)
+        loc.halo_exchange(Ql2)
+        loc.halo_exchange(ql)
+        ib.ghost_update_euler(loc, fl, Ql2, bcs)
+        loc.halo_exchange(Ql2)      # R = qR / rho at a donor that is itself a ghost cell uses its NEW density: refresh Q first
+        ib.ghost_update_rans(loc, Ql2, ql, rbc)
+        loc.halo_exchange(ql)
+        ib.residual_rans(loc, fl, Ql2, ql, Rl2, RRl, cl2)
     own = l2g[:n_owned]
+    okC5 = (np.array_equal(Rl2.to_host()[:n_owned], Rg2.to_host()[own]) and np.array_equal(RRl.to_host()[:n_owned], RRg.to_host()[own])
+            and np.array_equal(ql.to_host()[:n_owned], qg.to_host()[own]) and np.array_equal(cl2.to_host()[:n_owned], cg2.to_host()[own]))
+    if not okC5:
+        for lab, a, b in (("R5", Rl2.to_host()[:n_owned], Rg2.to_host()[own]), ("RR", RRl.to_host()[:n_owned], RRg.to_host()[own]),
+                          ("qR", ql.to_host()[:n_owned], qg.to_host()[own]), ("cfl", cl2.to_host()[:n_owned], cg2.to_host()[own])):
+            bad = np.flatnonzero((a != b).reshape(len(a), -1).any(axis=1))
+            print(f"[{label}] rank {rank}: C5 {lab}: {len(bad)} rows differ, max |diff| {np.abs(a - b).max():.3e} of scale {np.abs(b).max():.3e}; "
+                  f"first rows {bad[:6]}", flush=True)
     okR = np.array_equal(Rl.to_host()[:n_owned], Rg.to_host()[own])
     okc = np.array_equal(cl.to_host()[:n_owned], cg.to_host()[own])
     okQ = np.array_equal(Ql.to_host()[:n_owned], Qg.to_host()[own])
     dR = np.abs(Rl.to_host()[:n_owned] - Rg.to_host()[own]).max(axis=1)
     coupled = sorted(info.get("coupled_families", ()))
     print(f"[{label}] rank {rank}: owned {n_owned} halo {info['n_halo']} exchanged {len(need)} coupled {coupled} | first exchange {ok0} "
-          f"Q {okQ} R {okR} cfl {okc} overlapped-step {okF} (cells with R mismatch {(dR > 0).sum()})", flush=True)
-    ok = ok0 and okR and okc and okQ and okF and (bool(coupled) == expect_coupled)
+          f"Q {okQ} R {okR} cfl {okc} overlapped-step {okF} C5 {okC5} (cells with R mismatch {(dR > 0).sum()})", flush=True)
+    ok = ok0 and okR and okc and okQ and okF and okC5 and (bool(coupled) == expect_coupled)
     t = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return t.item() == 1
