@@ -2,13 +2,17 @@
 """Benchmark of the hot path: cell-updates/s of (IB ghost update of every boundary + full Euler residual).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (libibx, sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the restated reference path (NumPy oracle)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the restated reference path (compiled C + OpenMP, all host cores)
+    python bench.py --workload c5 [--gpus N]                 # secondary workload: swept-wing RANS residual (configs[4])
 
 Workload (BASELINE.json configs[3], SURVEY.md 8d "C4"): 3-D sphere octree, box (-16)^3..16^3, block_size 8,
 growth_ratio 2, wall = icosphere STL (6 subdivisions, 81 920 triangles, radius 0.5), finest cell width 32/2^10/8 inside Ball(0, r); r = 0.75
 gives 50.2 M cells on one GPU and is enlarged so that the cell count grows with the number of GPUs (weak
 scaling, ~50 M cells per GPU).  Inputs: the smooth synthetic state of SURVEY.md 8(d), seed 12345.
-One step = halo exchange + ghost update (wall, farfield) + halo exchange + residual on every rank.
+One step = [halo exchange +] ghost update (wall, farfield) [+ halo exchange] + residual on every rank, through
+ibx_step_euler / ibx_step_euler_sharded (exchanges and ghost update run on a second stream under ghost-free work).
+The JSON line also carries `fast_mode` (the price of the bit-exact arithmetic), `halo` (phase timings at N > 1), `e2e`
+(host buffers in and out, two evaluations in flight) and `cpu_baseline`.
 The working set (state 1 GB + residual 1.2 GB + scratch 1.2 GB per 50 M cells) is far larger than the 126 MB L2,
 so no explicit L2 flush is needed between timed iterations.
 """
