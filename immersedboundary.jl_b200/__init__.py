@@ -17,6 +17,6 @@ from .cfd import (Fluid, FlowBC, state2primitive, primitive2state, speed_of_soun
                   streamwise_direction, Reynolds_number, adjust_Reynolds,
                   residual_euler, residual_rans, step_euler, step_euler_sharded, ghost_update_euler, ghost_update_rans, residual_advection, euler_step_host, euler_step_host_begin,
                   euler_step_host_end, pinned_empty)
-from .solver import FAS, Multigrid, PIPreconditioner, hutchinson_trick, Linearization, linearize, proj_along, solve  # noqa: F401
+from .solver import FAS, march_euler, local_step_update, RK_STAGES, Multigrid, PIPreconditioner, hutchinson_trick, Linearization, linearize, proj_along, solve  # noqa: F401
 from .vtk import export_vtk, vtk_grid_mesh, vtk_grid_stl  # noqa: F401
 from . import synthetic, turbulence  # noqa: F401

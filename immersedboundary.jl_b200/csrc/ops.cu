@@ -413,6 +413,19 @@ __global__ void k_clamped_update(float* __restrict__ Q, const float* __restrict_
   }
 }
 
+// one stage of a local-time-step march: Q = Q0 + ((alpha / cfl_i) * R) * mask_i, in that order of roundings
+__global__ void k_local_step(const float* __restrict__ Q0, const float* __restrict__ R, const float* __restrict__ cfl,
+                             const float* __restrict__ mask, float alpha, float* __restrict__ Q, int64_t n, int cols) {
+  int64_t tot = n * cols;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = t % n;
+    float w = alpha / cfl[i];
+    float d = w * R[t];
+    if (mask) d = d * mask[i];
+    Q[t] = Q0[t] + d;
+  }
+}
+
 // ------------------------------------------------------------------ reductions: warp shuffle -> block -> one slot per block
 __device__ __forceinline__ double red_combine(int op, double a, double b) {
   switch (op) {
@@ -932,6 +945,26 @@ int ibx_clamped_update(ibx_ctx* c, ibx_array Q, ibx_array omega, ibx_array r) {
   GET_ARR(R, r);
   SHAPE(A.rows == R.rows && A.cols == R.cols && W.rows == A.rows && (W.cols == A.cols || W.cols == 1), "Q, r equal; omega rows x (1|nv)");
   k_clamped_update<<<GRID(A.rows * A.cols)>>>(A.p, W.p, (int)W.cols, R.p, A.rows, (int)A.cols);
+  LAUNCH_CHECK();
+  return IBX_OK;
+}
+
+int ibx_local_step_update(ibx_ctx* c, ibx_array Q0, ibx_array R, ibx_array cfl, ibx_array mask, float alpha, ibx_array Q) {
+  CHECK_CTX(c);
+  GET_ARR(A0, Q0);
+  GET_ARR(Rr, R);
+  GET_ARR(Cf, cfl);
+  GET_ARR(A, Q);
+  const float* m = nullptr;
+  if (mask) {
+    GET_ARR(Mk, mask);
+    SHAPE(Mk.rows == A.rows && Mk.cols == 1, "mask is rows x 1");
+    m = Mk.p;
+  }
+  SHAPE(A0.rows == A.rows && A0.cols == A.cols && Rr.rows == A.rows && Rr.cols == A.cols && Cf.rows == A.rows && Cf.cols == 1,
+        "Q0, R, Q equal; cfl rows x 1");
+  if (A.rows == 0) return IBX_OK;
+  k_local_step<<<GRID(A.rows * A.cols)>>>(A0.p, Rr.p, Cf.p, m, alpha, A.p, A.rows, (int)A.cols);
   LAUNCH_CHECK();
   return IBX_OK;
 }

@@ -24,7 +24,7 @@ export Stereolitography, merge_points, feature_regions, DistanceField, Ball, Box
        Fluid, FlowBC, state2primitive, primitive2state, speed_of_sound, inviscid_fluxes,
        residual_euler!, ghost_update_euler!, Transport, dynamic_viscosity, heat_conductivity, viscous_fluxes,
        shock_sensor, shear_rate, Ducros_sensor, pressure_coefficient, Accumulator, Interpolator, multigrid, FAS!,
-       euler_step_host!, euler_step_host_end, halo_begin!, halo_end!, wall_function, Smagorinsky_νSGS, standard_kϵ,
+       euler_step_host!, euler_step_host_end, step_euler!, march_euler!, local_step_update!, halo_begin!, halo_end!, wall_function, Smagorinsky_νSGS, standard_kϵ,
        Wray_Agarwal, WALE_νSGS
 
 const libibx = get(ENV, "LIBIBX", joinpath(@__DIR__, "..", "libibx.so"))
@@ -590,6 +590,30 @@ function step_euler!(dom::Domain, fluid::Fluid, bcs::Vector{Pair{String, FlowBC}
                         context(), dom.h, fluid, flux_kind, length(specs), specs, Q.h, R.h, cfl.h))
         end
     end
+end
+
+"`Q = Q0 + ((alpha / cfl) * R) * mask` in one kernel (`ibx_local_step_update`); `Q` may be `Q0`."
+local_step_update!(Q::IBXArray, Q0::IBXArray, R::IBXArray, cfl::IBXArray, alpha::Real; mask::Union{Nothing, IBXArray} = nothing) =
+    check(ccall((:ibx_local_step_update, libibx), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cfloat, Int64),
+                context(), Q0.h, R.h, cfl.h, isnothing(mask) ? 0 : mask.h, Float32(alpha), Q.h))
+
+"""Pseudo-time march with local time steps on the device: per step, ghost update in place, `Q0 = Q`, then for every
+multistage coefficient `a`: `step_euler!` and `Q = Q0 + a CFL R / cfl * live`.  `live` (0/1 per cell) freezes the ghost cells
+between residual evaluations (they only take boundary values)."""
+function march_euler!(dom::Domain, fluid::Fluid, bcs::Vector{Pair{String, FlowBC}}, Q::IBXArray, n_steps::Int;
+                      CFL::Real = 0.8f0, stages = (0.1481f0, 0.4f0, 1.0f0), live::Union{Nothing, IBXArray} = nothing, flux_kind::Int = 0)
+    R = similar(Q); cfl = IBXArray{1}((size(Q, 1),)); Q0 = similar(Q)
+    for _ = 1:n_steps
+        for (n, bc) in bcs
+            ghost_update_euler!(dom, fluid, n, bc, Q)
+        end
+        copyto!(Q0, Q)
+        for a in stages
+            step_euler!(dom, fluid, bcs, Q, R, cfl; flux_kind = flux_kind)
+            local_step_update!(Q, Q0, R, cfl, Float32(a) * Float32(CFL); mask = live)
+        end
+    end
+    Q
 end
 
 "Configuration C5: canonical RANS residual (`ibx_residual_rans`) and the ghost update of the transported variable."

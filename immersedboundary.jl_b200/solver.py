@@ -42,6 +42,42 @@ def FAS(f, Q, coarseners=(), prolongators=(), prescribed_f=None, multigrid_level
     return nr / (nr0 + EPS32)
 
 
+RK_STAGES = {1: (1.0,), 2: (0.5, 1.0), 3: (0.1481, 0.4, 1.0), 4: (0.25, 1.0 / 3.0, 0.5, 1.0), 5: (0.25, 1.0 / 6.0, 0.375, 0.5, 1.0)}
+
+
+def local_step_update(Q0, R, cfl, alpha, Q, mask=None):
+    """``Q = Q0 + ((alpha / cfl) * R) * mask`` in one kernel (``ibx_local_step_update``); ``Q`` may be ``Q0``."""
+    call("ibx_local_step_update", context(), Q0.h, R.h, cfl.h, 0 if mask is None else mask.h, float(F32(alpha)), Q.h)
+    return Q
+
+
+def march_euler(dom, fluid, bcs, Q, n_steps, CFL=0.8, stages=3, live=None, flux="hll", monitor=None, every=0):
+    """Pseudo-time march of the Euler residual with local time steps, the driver loop the reference leaves to its users
+    (``test/advection.jl:28-46`` applies the BCs to the marched state and advances it by ``R * CFL / cfl``; ``FAS!``
+    with ``f(l, Q) = (R .* CFL ./ cfl, 1)``, ``src/solver.jl:78-82``, is the single-stage case).
+
+    Per step: ghost update of ``Q`` in place, ``Q0 = Q``, then for each multistage coefficient ``a``:
+    ``step_euler`` (ghost update + residual) and ``Q = Q0 + a CFL R / cfl * live``.  ``live`` (N x 1 of 0/1) freezes
+    cells between residual evaluations -- the ghost cells, which only ever take boundary values: a ghost cell advanced by
+    its own residual drifts, and so does every image point that interpolates from it.  Everything runs on the device;
+    ``monitor(step, Q, R, cfl)`` is called every ``every`` steps with the arrays of the last stage."""
+    from . import cfd
+
+    alphas = RK_STAGES[stages] if isinstance(stages, int) else tuple(stages)
+    R = DeviceArray(Q.rows, Q.cols, False)
+    cf = DeviceArray(Q.rows, 1, True)
+    Q0 = Q.like()
+    for it in range(n_steps):
+        cfd.ghost_update_euler(dom, fluid, Q, bcs)
+        Q0.assign(Q)
+        for a in alphas:
+            cfd.step_euler(dom, fluid, bcs, Q, R, cf, flux)
+            local_step_update(Q0, R, cf, float(F32(a) * F32(CFL)), Q, live)
+        if monitor is not None and every and (it + 1) % every == 0:
+            monitor(it + 1, Q, R, cf)
+    return Q
+
+
 class Multigrid:
     """``GeometricMultigrid.Multigrid(X, n_levels, volumes)`` (``src/mgrid.jl:104-144``)."""
 

@@ -122,3 +122,19 @@ def swept_wing(n_chord=64, n_span=64, chord=1.0, span=4.0, sweep_deg=30.0, thick
                 if len(set(t)) == 3:
                     tri.append(t[::-1] if flip else t)
     return pts.astype(F32), np.asarray(tri, dtype=np.int64)
+
+
+def inside_polygon(poly, pts):
+    """Even-odd ray casting: which of ``pts`` (n, 2) lie inside the closed loop ``poly`` (m, 2)?  Used to start the cells
+    enclosed by a 2-D body at rest (they form a closed cavity the immersed boundary never flushes)."""
+    x, y = pts[:, 0].astype(np.float64), pts[:, 1].astype(np.float64)
+    inside = np.zeros(len(pts), bool)
+    n = len(poly)
+    for i in range(n):
+        (x0, y0), (x1, y1) = poly[i], poly[(i + 1) % n]
+        if y0 == y1:
+            continue
+        cond = (y0 > y) != (y1 > y)
+        xi = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+        inside ^= cond & (x < xi)
+    return inside

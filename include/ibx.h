@@ -327,6 +327,10 @@ int ibx_ew_scalar(ibx_ctx* c, int op, ibx_array a, float s, int scalar_first, ib
 int ibx_ew_unary(ibx_ctx* c, int op, ibx_array a, ibx_array out);
 int ibx_axpy(ibx_ctx* c, float alpha, ibx_array x, ibx_array y);                 /* y += alpha * x */
 int ibx_clamped_update(ibx_ctx* c, ibx_array Q, ibx_array omega, ibx_array r);   /* Q += clamp(omega,0,1) * r (solver.jl:82) */
+/* One stage of a local-time-step march, Q = Q0 + ((alpha / cfl_i) * R) * mask_i  (mask = 0: no mask).  This is the update
+ * the reference's drivers write as broadcasts around `FAS!`'s f(l, Q) = (R .* CFL ./ cfl, 1) (src/solver.jl:78-82,
+ * test/advection.jl:28-46); Q may alias Q0. */
+int ibx_local_step_update(ibx_ctx* c, ibx_array Q0, ibx_array R, ibx_array cfl, ibx_array mask, float alpha, ibx_array Q);
 /* op: 0 sum, 1 max, 2 min, 3 max|.|, 4 sum of squares (double accumulation); one value per column, or over
  * everything when per_column = 0 */
 int ibx_reduce(ibx_ctx* c, int op, ibx_array a, int per_column, double* out);
