@@ -4,11 +4,13 @@ doing the same march, then lift / drag from the surface pressure integral (Surfa
 surface_integral).  Tolerances asserted below: state within 5e-4 of its per-variable scale, lift and drag coefficients
 within 1e-4 (the north-star figure for Cl / Cd).
 
-The reference ships no Euler residual and no time integrator, so there is no converged reference polar
-to compare with; the canonical residual of SURVEY.md A.10 marched from an impulsive start loses its ghost-cell values
-next to the thin trailing edge after ~28 steps in the ORACLE as well (DESIGN.md section 7 localises it).  The comparison
-is therefore made on the transient after 20 steps, where both paths have processed the same 20 ghost updates +
-residuals; the 2e-6 difference of the ghost-interpolation weights is amplified to ~1e-4 of the state scale by then."""
+The reference ships no Euler residual and no time integrator.  This file keeps the round-1 comparison on
+the start-up transient of the plain forward-Euler march in which EVERY cell -- ghost cells included -- is advanced by
+its residual; that driver loses its ghost-cell values next to the thin trailing edge after ~28 steps in the ORACLE as
+well (a ghost cell advanced by its own residual drifts, and image points interpolate from it).
+The converged polar is in tests/test_rae2822_converged_gpu.py (ghost cells frozen between residual evaluations).  Here
+both paths have processed the same 20 ghost updates + residuals; the 2e-6 difference of the ghost-interpolation weights
+is amplified to ~1e-4 of the state scale by then."""
 import numpy as np
 import pytest
 
