@@ -26,7 +26,7 @@ struct BlockIndex {
   int nd, bs;
   int64_t nb, cpb;
   const float *bo, *bw;     // block origins / widths (nb x nd)
-  const float* centers;     // cell centres (ncells x nd)
+  CellGeom geo;             // cell centres / widths, computed from the block tables (same bits as get_cells' arrays)
   struct Class {
     float w[3];
     double R;
@@ -35,14 +35,14 @@ struct BlockIndex {
   };
   std::vector<Class> classes;
 
-  void build(const ibx_mesh& m, const float* cell_centers) {
+  void build(const ibx_mesh& m) {
     nd = m.nd;
     bs = m.block_size;
     nb = m.nblocks();
     cpb = m.cells_per_block();
     bo = m.block_origins.data();
     bw = m.block_widths.data();
-    centers = cell_centers;
+    geo.init(m);
     std::map<std::vector<float>, int> key2class;
     std::vector<std::vector<double>> pts;
     for (int64_t b = 0; b < nb; ++b) {
@@ -123,13 +123,19 @@ struct BlockIndex {
           if (lo[d] > hi[d]) empty = true;
         }
         if (empty) continue;
-        for (int i2 = lo[2]; i2 <= (nd > 2 ? hi[2] : 0); ++i2)
-          for (int i1 = lo[1]; i1 <= hi[1]; ++i1)
+        float cc[3] = {0.f, 0.f, 0.f};
+        for (int i2 = lo[2]; i2 <= (nd > 2 ? hi[2] : 0); ++i2) {
+          if (nd > 2) cc[2] = geo.cb(b, i2, 2);
+          for (int i1 = lo[1]; i1 <= hi[1]; ++i1) {
+            cc[1] = geo.cb(b, i1, 1);
             for (int i0 = lo[0]; i0 <= hi[0]; ++i0) {
               int64_t cell = b * cpb + i0 + (int64_t)bs * (i1 + (int64_t)bs * i2);
-              float dd = d2f(centers + cell * nd, x, nd);
+              cc[0] = geo.cb(b, i0, 0);
+              float dd = d2f(cc, x, nd);
               if (dd <= r2) cand.emplace_back(dd, cell);
             }
+          }
+        }
       }
       if ((int)cand.size() >= k) {
         std::partial_sort(cand.begin(), cand.begin() + k, cand.end());
@@ -207,8 +213,9 @@ static void build_faces(ibx_domain& D, const BlockIndex& bi, bool want_faces) {
   const ibx_mesh& m = *D.mesh;
   int nd = D.nd, bs = D.block_size;
   int64_t nb = bi.nb, cpb = bi.cpb;
-  const float* C = D.centers.data();
+  const float* C = D.centers.data();   // per-cell arrays: only read below when the face lists are wanted
   const float* W = D.widths.data();
+  if (want_faces && D.centers.empty()) throw std::runtime_error("face lists need the per-cell arrays (not a rank-restricted build)");
   // --- block-face connectivity + candidate (+ side) neighbours of every block
   D.block_faces.assign((size_t)nb * 2 * nd, BlockFace{0, {-1, -1, -1, -1}, {0, 0}});
   D.block_h.resize((size_t)nb * nd);
@@ -471,13 +478,19 @@ static inline float diam_of(const float* w, int nd) {
 }
 
 // linear_weights (src/nninterp.jl:16-42) / IDW_weights (:47-69) about the point x for donors idx[0..k)
-static int stencil_weights(const float* C, int nd, const int64_t* idx, int k, const float* x, bool linear,
+struct CloudPoints {  // donors of an arbitrary point cloud (row-major n x nd)
+  const float* X;
+  int nd;
+  inline float c(int64_t i, int d) const { return X[i * nd + d]; }
+};
+template <class Donors>   // CellGeom (cells of the mesh) or CloudPoints
+static int stencil_weights(const Donors& C, int nd, const int64_t* idx, int k, const float* x, bool linear,
                            int64_t* oidx, float* ow) {
   float w[16], dX[16 * 3];
   for (int j = 0; j < k; ++j) {
     float acc = 0.f;
     for (int d = 0; d < nd; ++d) {
-      float df = C[idx[j] * nd + d] - x[d];
+      float df = C.c(idx[j], d) - x[d];
       dX[j * nd + d] = df;
       float sq = df * df;
       acc = d == 0 ? sq : acc + sq;
@@ -514,8 +527,7 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
   // boundary_partitions (src/ImmersedBoundary.jl:456-476) + Boundary (:422-448)
   int nd = D.nd;
   int k = 1 << nd;
-  const float* C = D.centers.data();
-  const float* W = D.widths.data();
+  const CellGeom& C = bi.geo;
   int64_t G = (int64_t)ghosts.size();
   for (int64_t s = 0; s < G; s += max_part) {
     int64_t e = std::min(G, s + max_part), n = e - s;
@@ -534,12 +546,14 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
       int64_t c = B.ghost[g];
       float nrm[3], acc = 0.f, img[3];
       for (int d = 0; d < nd; ++d) {
-        nrm[d] = C[c * nd + d] - B.proj[g * nd + d];
+        nrm[d] = C.c(c, d) - B.proj[g * nd + d];
         float sq = nrm[d] * nrm[d];
         acc = d == 0 ? sq : acc + sq;
       }
       float gd = std::sqrt(acc);
-      float idist = diam_of(W + c * nd, nd) * ghost_ratio + EPS32;
+      float wc[3];
+      C.width(c, wc);
+      float idist = diam_of(wc, nd) * ghost_ratio + EPS32;
       for (int d = 0; d < nd; ++d) {
         nrm[d] = nrm[d] / (gd + EPS32);
         B.normals[g * nd + d] = nrm[d];
@@ -550,7 +564,7 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
       B.image_dist[g] = idist;
       int64_t idx[17];
       float dd[17];
-      double cw = std::max({(double)W[c * nd], (double)W[c * nd + 1], nd > 2 ? (double)W[c * nd + 2] : 0.0});
+      double cw = std::max({(double)wc[0], (double)wc[1], nd > 2 ? (double)wc[2] : 0.0});
       // one candidate more than needed: a k-th / (k+1)-th distance tie is the only place where NearestNeighbors.jl's
       // traversal order (not reproducible) could select another donor than the (distance, index) rule
       int found = bi.knn(img, k + 1, 1.5 * cw, idx, dd);
@@ -580,47 +594,42 @@ static void build_boundary(ibx_domain& D, const BlockIndex& bi, const std::vecto
   }
 }
 
-static void ghosts_hcube(const ibx_domain& D, const std::vector<std::pair<int, int>>& faces, float glr,
+static void ghosts_hcube(const ibx_domain& D, const CellGeom& C, const std::vector<std::pair<int, int>>& faces, float glr,
                          std::vector<int32_t>& ghosts, std::vector<float>& projs, int64_t r0, int64_t r1) {
-  // src/ImmersedBoundary.jl:258-305
+  // src/ImmersedBoundary.jl:258-305; only the cells of [r0, r1) are examined (and only they get scratch)
   int nd = D.nd;
   const ibx_mesh& m = *D.mesh;
-  const float* C = D.centers.data();
-  const float* W = D.widths.data();
-  int64_t N = D.ncells;
-  std::vector<uint8_t> mask(N, 0);
-  std::vector<int8_t> which(N, -1);
+  const int64_t n = r1 - r0;
+  std::vector<uint8_t> mask((size_t)n, 0);
+  std::vector<int8_t> which((size_t)n, -1);
 #pragma omp parallel for schedule(static)
   for (int64_t i = r0; i < r1; ++i) {
     float best = INFINITY;
-    float lim = diam_of(W + i * nd, nd) * glr;
+    float wi[3];
+    C.width(i, wi);
+    float lim = diam_of(wi, nd) * glr;
     for (size_t f = 0; f < faces.size(); ++f) {
       int dim = faces[f].first;
       float plane = faces[f].second ? (m.origin[dim] + m.widths[dim]) : m.origin[dim];
-      float df = plane - C[i * nd + dim];
+      float df = plane - C.c(i, dim);
       float ds = std::sqrt(df * df);
-      if (ds < best) { best = ds; which[i] = (int8_t)f; }
-      if (ds < lim) mask[i] = 1;
+      if (ds < best) { best = ds; which[i - r0] = (int8_t)f; }
+      if (ds < lim) mask[i - r0] = 1;
     }
   }
   for (int64_t i = r0; i < r1; ++i)
-    if (mask[i]) {
+    if (mask[i - r0]) {
       ghosts.push_back((int32_t)i);
-      int dim = faces[which[i]].first;
-      float plane = faces[which[i]].second ? (m.origin[dim] + m.widths[dim]) : m.origin[dim];
-      for (int d = 0; d < nd; ++d) projs.push_back(d == dim ? plane : C[i * nd + d]);
+      int dim = faces[which[i - r0]].first;
+      float plane = faces[which[i - r0]].second ? (m.origin[dim] + m.widths[dim]) : m.origin[dim];
+      for (int d = 0; d < nd; ++d) projs.push_back(d == dim ? plane : C.c(i, d));
     }
 }
 
-static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr, std::vector<int32_t>& ghosts,
+static void ghosts_surface(const ibx_domain& D, const CellGeom& C, const ibx_dfield& df, float glr, std::vector<int32_t>& ghosts,
                            std::vector<float>& projs, int64_t r0, int64_t r1) {
   // src/ImmersedBoundary.jl:194-230
   int nd = D.nd;
-  const float* C = D.centers.data();
-  const float* W = D.widths.data();
-  int64_t N = D.ncells;
-  std::vector<uint8_t> keep(N, 0);
-  std::vector<float> pr((size_t)N * 0);
   std::vector<std::vector<float>> tproj(omp_get_max_threads());
   std::vector<std::vector<int32_t>> tghost(omp_get_max_threads());
 #pragma omp parallel
@@ -631,8 +640,11 @@ static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr,
 #pragma omp for schedule(dynamic, 4096)
     for (int64_t i = r0; i < r1; ++i) {
       double x[3];
-      for (int d = 0; d < nd; ++d) x[d] = C[i * nd + d];
-      float diam = diam_of(W + i * nd, nd);
+      float ci[3], wi[3];
+      C.center(i, ci);
+      C.width(i, wi);
+      for (int d = 0; d < nd; ++d) x[d] = ci[d];
+      float diam = diam_of(wi, nd);
       float lim2 = diam * glr * 2.0f;
       Num dist;
       if (!df.distance_within(x, true, (double)lim2, &dist)) continue;   // == !(df.distance(x) <= lim2), src/ImmersedBoundary.jl:208
@@ -641,7 +653,7 @@ static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr,
       float pf[3], acc = 0.f;
       for (int d = 0; d < nd; ++d) {
         pf[d] = (float)p[d];
-        float dfv = pf[d] - C[i * nd + d];
+        float dfv = pf[d] - ci[d];
         float sq = dfv * dfv;
         acc = d == 0 ? sq : acc + sq;
       }
@@ -663,8 +675,9 @@ static void ghosts_surface(const ibx_domain& D, const ibx_dfield& df, float glr,
   }
 }
 
-static void build_interp(const BlockIndex& bi, const float* C, int nd, int64_t q, const float* Xc, const float* bias,
+static void build_interp(const BlockIndex& bi, int nd, int64_t q, const float* Xc, const float* bias,
                          bool linear, ibx_accum& out) {
+  const CellGeom& C = bi.geo;
   // Interpolator over the domain's own cells (src/nninterp.jl:85-138)
   int k = 1 << nd;
   std::vector<int64_t> sidx((size_t)q * k);
@@ -718,9 +731,13 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
   D->mesh = m;
   D->ncells = m->ncells();
   int nd = D->nd;
-  D->centers.resize((size_t)D->ncells * nd);
-  D->widths.resize((size_t)D->ncells * nd);
-  mesh_cells(*m, D->centers.data(), D->widths.data());
+  // a rank-restricted build (input of ibx_domain_shard) never holds per-cell arrays of the GLOBAL mesh: every centre /
+  // width the ghost search needs is computed from the block tables (CellGeom), the shard fills its own local arrays
+  if (nranks == 1) {
+    D->centers.resize((size_t)D->ncells * nd);
+    D->widths.resize((size_t)D->ncells * nd);
+    mesh_cells(*m, D->centers.data(), D->widths.data());
+  }
   // the reference prints its build phases when `verbose` (src/ImmersedBoundary.jl:589,705,767); here: IBX_BUILD_VERBOSE=1
   const bool verbose = getenv("IBX_BUILD_VERBOSE") != nullptr;
   double t_phase = omp_get_wtime();
@@ -729,7 +746,7 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
     t_phase = omp_get_wtime();
   };
   BlockIndex bi;
-  bi.build(*m, D->centers.data());
+  bi.build(*m);
   phase("cells + block index");
   build_faces(*D, bi, build_partitions_flag != 0);
   phase("faces / block contacts");
@@ -744,7 +761,7 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
     }
     std::vector<int32_t> ghosts;
     std::vector<float> projs;
-    ghosts_hcube(*D, faces, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
+    ghosts_hcube(*D, bi.geo, faces, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
     phase("hypercube ghosts");
     BoundaryFamily fam;
     fam.name = fam_names[f];
@@ -756,7 +773,7 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
     const ibx_dfield& df = *m->surf_fields[s];
     std::vector<int32_t> ghosts;
     std::vector<float> projs;
-    ghosts_surface(*D, df, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
+    ghosts_surface(*D, bi.geo, df, ghost_layer_ratio, ghosts, projs, g_r0, g_r1);
     phase("surface ghosts + projections");
     BoundaryFamily fam;
     fam.name = m->surf_names[s];
@@ -788,7 +805,9 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
       int64_t ci;
       float dd;
       bi.knn(x, 1, 1.5 * bi.local_width(x), &ci, &dd);
-      float h = diam_of(&D->widths[ci * nd], nd) * 1.01f;
+      float wci[3];
+      bi.geo.width(ci, wci);
+      float h = diam_of(wci, nd) * 1.01f;
       float A = std::sqrt(acc) + EPS32;
       S.offsets[p] = h;
       S.areas[p] = A;
@@ -799,8 +818,8 @@ static int domain_build_impl(const ibx_mesh* mh, int64_t max_partition_size, int
         off_pts[p * nd + d] = x[d] + bias[p * nd + d] * ghost_layer_ratio;
       }
     }
-    build_interp(bi, D->centers.data(), nd, np, S.points.data(), bias.data(), true, S.interp);
-    build_interp(bi, D->centers.data(), nd, np, off_pts.data(), nullptr, true, S.offset_interp);
+    build_interp(bi, nd, np, S.points.data(), bias.data(), true, S.interp);
+    build_interp(bi, nd, np, off_pts.data(), nullptr, true, S.offset_interp);
   }
   g_dom[D.get()] = D;
   *out = D.get();
@@ -875,6 +894,10 @@ int ibx_domain_faces(const ibx_domain* d, int32_t* faces3) {
 int ibx_domain_cells(const ibx_domain* d, float* centers, float* widths) {
   IBX_TRY
   DOM(d);
+  if (D.centers.empty() && D.ncells > 0) {   // rank-restricted global build: nothing stored, compute on request
+    mesh_cells(*D.mesh, centers, widths);
+    return IBX_OK;
+  }
   if (centers) std::copy(D.centers.begin(), D.centers.end(), centers);
   if (widths) std::copy(D.widths.begin(), D.widths.end(), widths);
   return IBX_OK;
@@ -1052,7 +1075,7 @@ int ibx_interpolator_build(int nd, int64_t n, const float* X, int64_t q, const f
     int64_t idx[16];
     double dd[16];
     int found = tree.knn(xq, true, k, idx, dd);
-    cnt[p + 1] = stencil_weights(X, nd, idx, found, Xc + p * nd, linear != 0, &sidx[p * k], &sw[p * k]);
+    cnt[p + 1] = stencil_weights(CloudPoints{X, nd}, nd, idx, found, Xc + p * nd, linear != 0, &sidx[p * k], &sw[p * k]);
   }
   for (int64_t p = 0; p < q; ++p) cnt[p + 1] += cnt[p];
   A->n_out = q;

@@ -132,6 +132,40 @@ struct ibx_accum {
 
 namespace ibx {
 
+// Centre / width of any cell straight from the block tables, with get_cells' float32 operations
+// (src/mesher.jl:1064-1112): centre = fl(fl((i + 1/2) / bs) * block_width) + block_origin, width = block_width / bs.
+// mesh_cells() fills its arrays through this, so an array entry and a value computed on the fly are the same bits;
+// a rank-restricted Domain build (ibx_domain_build_for_rank) never materialises the global arrays.
+struct CellGeom {
+  const float *bo = nullptr, *bw = nullptr;
+  int nd = 0, bs = 0, bs2 = 0;
+  int64_t cpb = 0;
+  float ic[64];
+  void init(const ibx_mesh& m) {
+    bo = m.block_origins.data();
+    bw = m.block_widths.data();
+    nd = m.nd;
+    bs = m.block_size;
+    bs2 = bs * bs;
+    cpb = m.cells_per_block();
+    for (int i = 0; i < bs && i < 64; ++i) ic[i] = ((float)i + 0.5f) / (float)bs;
+  }
+  // centre along d of the cell with index i along d in block b
+  inline float cb(int64_t b, int i, int d) const {
+    float prod = ic[i] * bw[b * nd + d];
+    return prod + bo[b * nd + d];
+  }
+  inline float c(int64_t cell, int d) const {
+    const int64_t b = cell / cpb;
+    const int l = (int)(cell - b * cpb);
+    const int i = d == 0 ? l % bs : (d == 1 ? (l / bs) % bs : l / bs2);
+    return cb(b, i, d);
+  }
+  inline float w(int64_t cell, int d) const { return bw[(cell / cpb) * nd + d] / (float)bs; }
+  inline void center(int64_t cell, float* out) const { for (int d = 0; d < nd; ++d) out[d] = c(cell, d); }
+  inline void width(int64_t cell, float* out) const { for (int d = 0; d < nd; ++d) out[d] = w(cell, d); }
+};
+
 struct FaceTable {  // per partition, per dim
   std::vector<int32_t> owners, neighbors;
   std::vector<int32_t> lptr, lidx, rptr, ridx;  // left/right face lists, CSR over domain cells

@@ -87,29 +87,34 @@ static void refine_octree(const std::vector<Criterion>& crit, int nd, const floa
   }
 }
 
-void mesh_cells(const ibx_mesh& m, float* centers, float* widths) {
-  // get_cells, margin = 0 (src/mesher.jl:1064-1112): block-major, first dim fastest in a block
-  int nd = m.nd, bs = m.block_size;
-  int64_t cpb = m.cells_per_block(), nb = m.nblocks();
-  std::vector<float> ic(bs);
-  for (int i = 0; i < bs; ++i) ic[i] = ((float)i + 0.5f) / (float)bs;
-#pragma omp parallel for schedule(static)
-  for (int64_t b = 0; b < nb; ++b) {
-    const float* bo = &m.block_origins[b * nd];
-    const float* bw = &m.block_widths[b * nd];
-    float cw[3];
-    for (int d = 0; d < nd; ++d) cw[d] = bw[d] / (float)bs;
-    for (int64_t l = 0; l < cpb; ++l) {
-      int64_t rem = l;
-      for (int d = 0; d < nd; ++d) {
-        int i = (int)(rem % bs);
-        rem /= bs;
-        float prod = ic[i] * bw[d];
-        if (centers) centers[(b * cpb + l) * nd + d] = prod + bo[d];
-        if (widths) widths[(b * cpb + l) * nd + d] = cw[d];
-      }
+// get_cells, margin = 0 (src/mesher.jl:1064-1112) for ONE block: cpb x nd centres / widths, first dim fastest.  The
+// float32 operations are CellGeom's (ibx_internal.h): the builder evaluates the same expressions cell by cell.
+void mesh_block_cells(const ibx_mesh& m, int64_t b, float* centers, float* widths) {
+  CellGeom G;
+  G.init(m);
+  const int nd = m.nd;
+  const int64_t cpb = m.cells_per_block();
+  const int bs = m.block_size;
+  float cw[3] = {0.f, 0.f, 0.f};
+  for (int d = 0; d < nd; ++d) cw[d] = G.w(b * cpb, d);
+  for (int64_t l = 0; l < cpb; ++l) {
+    int rem = (int)l;
+    for (int d = 0; d < nd; ++d) {
+      const int i = rem % bs;
+      rem /= bs;
+      if (centers) centers[l * nd + d] = G.cb(b, i, d);
+      if (widths) widths[l * nd + d] = cw[d];
     }
   }
+}
+
+void mesh_cells(const ibx_mesh& m, float* centers, float* widths) {
+  // block-major, first dim fastest in a block
+  int nd = m.nd;
+  int64_t cpb = m.cells_per_block(), nb = m.nblocks();
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < nb; ++b)
+    mesh_block_cells(m, b, centers ? centers + b * cpb * nd : nullptr, widths ? widths + b * cpb * nd : nullptr);
 }
 
 }  // namespace ibx
@@ -141,7 +146,7 @@ int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf,
                     int block_size, ibx_mesh** out) {
   IBX_TRY
   IBX_REQUIRE(nd == 2 || nd == 3, "nd must be 2 or 3");
-  IBX_REQUIRE(block_size >= 1, "block_size must be positive");
+  IBX_REQUIRE(block_size >= 1 && block_size <= 64, "block_size must be in 1 .. 64");
   auto m = std::make_shared<ibx_mesh>();
   m->nd = nd;
   m->block_size = block_size;
@@ -223,7 +228,7 @@ int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf,
 int ibx_mesh_from_blocks(const ibx_mesh* like, int block_size, ibx_mesh** out) {
   IBX_TRY
   auto src = lookup_mesh(like);
-  IBX_REQUIRE(block_size >= 1, "block_size must be positive");
+  IBX_REQUIRE(block_size >= 1 && block_size <= 64, "block_size must be in 1 .. 64");
   auto m = std::make_shared<ibx_mesh>(*src);
   m->block_size = block_size;
   g_mesh[m.get()] = m;

@@ -13,6 +13,7 @@
 namespace ibx {
 ibx_domain* find_domain(const ibx_domain* d);
 ibx_domain* register_domain(std::shared_ptr<ibx_domain> d);
+void mesh_block_cells(const ibx_mesh& m, int64_t b, float* centers, float* widths);
 
 // host mirror of the device-side neighbour lookup in fused.cu
 static int host_neighbors(const ibx_domain& D, int64_t cpb, int64_t cell, int d, int side, int64_t* out) {
@@ -182,8 +183,7 @@ int ibx_domain_shard(const ibx_domain* gh, int rank, int nranks, ibx_domain** ou
   S.local_to_global.resize((size_t)L->ncells);
   for (int64_t k = 0; k < nlb; ++k) {
     int64_t gb = lblocks[k];
-    std::copy(G.centers.begin() + gb * cpb * nd, G.centers.begin() + (gb + 1) * cpb * nd, L->centers.begin() + k * cpb * nd);
-    std::copy(G.widths.begin() + gb * cpb * nd, G.widths.begin() + (gb + 1) * cpb * nd, L->widths.begin() + k * cpb * nd);
+    mesh_block_cells(*G.mesh, gb, L->centers.data() + k * cpb * nd, L->widths.data() + k * cpb * nd);
     for (int d = 0; d < nd; ++d) L->block_h[k * nd + d] = G.block_h[gb * nd + d];
     for (int64_t l = 0; l < cpb; ++l) S.local_to_global[k * cpb + l] = (int32_t)(gb * cpb + l);
     for (int f = 0; f < 2 * nd; ++f) {

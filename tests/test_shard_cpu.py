@@ -143,3 +143,48 @@ def test_boundary_families_coupled_across_ranks_are_detected(ib):
         infos = _shard_all(ib, close, fams, world)
         assert all(i["coupled_families"] == infos[0]["coupled_families"] for i in infos)
         assert ("farfield", "wall") in infos[0]["coupled_families"] or ("wall", "farfield") in infos[0]["coupled_families"]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rank_restricted_build_gives_the_same_shard(ib, world):
+    """`Domain(..., for_rank=(rank, world))` (ibx_domain_build_for_rank: ghosts searched in the rank's block range only,
+    no per-cell array of the global mesh is ever allocated) followed by `.shard(rank, world)` must give the tables that
+    sharding the full global build gives: cells, ghosts, projections, donors and weights, halo request lists."""
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    pts, tri = ib.synthetic.icosphere(1, 0.5)
+    m = ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Stereolitography(pts, tri), F32(0.12)),
+                refinement_regions=[(ib.Ball([0, 0, 0], 0.9), F32(0.24))])
+    full = ib.Domain(m, hypercube_families=fams, build_partitions=False, build_surfaces=False, upload=False)
+    cen, wid = full.cells()
+    # the shard's send lists need every rank's requests: build all shards of both kinds first
+    a = [full.shard(r, world, all_gather_object=lambda obj: [obj] * world) for r in range(world)]
+    b = []
+    for r in range(world):
+        g = ib.Domain(m, max_partition_size=len(m), hypercube_families=fams, build_partitions=False, build_surfaces=False,
+                      upload=False, for_rank=(r, world))
+        assert len(g) == len(full)
+        gc, gw = g.cells()                                   # computed on request from the block tables
+        assert np.array_equal(gc, cen) and np.array_equal(gw, wid)
+        b.append(g.shard(r, world, all_gather_object=lambda obj: [obj] * world))
+    for r in range(world):
+        A, B = a[r], b[r]
+        ia, ib_ = A.shard_info, B.shard_info
+        assert (ia["n_owned"], ia["n_halo"], ia["owned_start"]) == (ib_["n_owned"], ib_["n_halo"], ib_["owned_start"])
+        assert np.array_equal(ia["local_to_global"], ib_["local_to_global"])
+        for peer in range(world):
+            assert np.array_equal(ia["requests"][peer], ib_["requests"][peer])
+        ca, wa = A.cells()
+        cb, wb = B.cells()
+        assert np.array_equal(ca, cb) and np.array_equal(wa, wb)
+        assert np.array_equal(ca, cen[ia["local_to_global"]])
+        assert np.array_equal(A.block_faces(), B.block_faces())
+        n_ghost = 0
+        for name in A.boundaries:
+            assert list(A.boundaries[name]) == list(B.boundaries[name])
+            for key, x in A.boundaries[name].items():
+                y = B.boundaries[name][key]
+                n_ghost += len(x.ghost_indices)
+                for field in ("ghost_indices", "image_domain", "projections", "normals_host", "image_distances", "ghost_distances",
+                              "interp_ptr", "interp_idx", "interp_w"):
+                    assert np.array_equal(getattr(x, field), getattr(y, field)), (name, field)
+        assert n_ghost > 100

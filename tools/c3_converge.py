@@ -96,6 +96,7 @@ def main():
     live = (~ghost if not args.evolve_ghosts else np.ones(N, bool)).astype(F32)[:, None]
     t0 = time.time()
     r0 = None
+    hist = []
     for it in range(args.steps + 1):
         if args.ramp:
             fac = F32(min(1.0, 0.2 + 0.8 * it / args.ramp))
@@ -118,7 +119,10 @@ def main():
             return
         Qprev = Q
         if it % args.every == 0:
-            Rr, c = resid(Q)
+            Qm = Q.copy(order="F")                      # monitor on a copy: a second ghost update would perturb the march
+            ref.ghost_update(fl, Qm, bcs, args.threads)
+            ref.residual(fl, Qm, R, cf, args.threads, use_sensor=not args.no_sensor)
+            Rr, c = R, cf
             nr = float(np.linalg.norm(((Rr / c[:, None]) * live)[:, 0]))
             r0 = r0 or nr
             try:
@@ -128,10 +132,14 @@ def main():
                 if it == 0:
                     print("coeffs unavailable:", e)
             rho = Q[:, 0]
+            hist.append((done + it + 1, nr, cl, cd))
             print(f"step {it:6d}  |R_rho/cfl| {nr:.4e}  ratio {nr / r0:.3e}  Cl {cl:+.6f}  Cd {cd:+.6f}  rho[min,max]=({rho.min():.3f},{rho.max():.3f})  t={time.time() - t0:.0f}s", flush=True)
     if args.save:
         cl, cd = coeffs(Q)
-        np.savez_compressed(args.save, Q=Q, cl=cl, cd=cd, steps=done + args.steps + 1, stages=args.stages, cfl=args.cfl, mach=args.mach, alpha=args.alpha)
+        h = np.array(hist)
+        last = h[h[:, 0] > (done + args.steps + 1) * 2 // 3]
+        np.savez_compressed(args.save, Q=Q, cl=cl, cd=cd, steps=done + args.steps + 1, history=h,
+                            cl_drift=float(np.ptp(last[:, 2])), cd_drift=float(np.ptp(last[:, 3])), command=" ".join(sys.argv), stages=args.stages, cfl=args.cfl, mach=args.mach, alpha=args.alpha)
 
 
 if __name__ == "__main__":
