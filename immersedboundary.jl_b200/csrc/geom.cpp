@@ -7,6 +7,8 @@
 #include <sstream>
 #include <unordered_map>
 #include <numeric>
+#include <cstdlib>
+#include <omp.h>
 
 namespace ibx {
 
@@ -27,10 +29,20 @@ void KDTree::build(int nd_, int64_t n_, const double* p, bool f32_) {
   pts.assign(p, p + n * nd);
   perm.resize(n);
   std::iota(perm.begin(), perm.end(), (int64_t)0);
-  nodes.clear();
-  bbox.clear();
-  nodes.reserve((size_t)(2 * n / kLeaf + 4));
-  if (n > 0) build_rec(0, n);
+  // a node that splits has more than kLeaf points and halves, so a leaf holds at least (kLeaf + 1) / 2 of them: the
+  // arrays are sized for the worst case up front and node ids are drawn from a counter, which lets the two halves of
+  // a large node be built by different threads (ids depend on the schedule, the tree and every query result do not)
+  const int64_t cap = 2 * (n / ((kLeaf + 1) / 2)) + 16;
+  nodes.assign((size_t)cap, Node{-1, 0.0, 0, 0, -1, -1});
+  bbox.assign((size_t)cap * 2 * nd, 0.0);
+  n_nodes_ = 0;
+  if (n > 0) {
+#pragma omp parallel
+#pragma omp single
+    build_rec(0, n);
+  }
+  nodes.resize((size_t)n_nodes_);
+  bbox.resize((size_t)n_nodes_ * 2 * nd);
 }
 
 void KDTree::build_f(int nd_, int64_t n_, const float* p) {
@@ -40,9 +52,10 @@ void KDTree::build_f(int nd_, int64_t n_, const float* p) {
 }
 
 int64_t KDTree::build_rec(int64_t lo, int64_t hi) {
-  int64_t id = (int64_t)nodes.size();
-  nodes.push_back({-1, 0.0, lo, hi, -1, -1});
-  bbox.resize((size_t)(id + 1) * 2 * nd);
+  int64_t id;
+#pragma omp atomic capture
+  id = n_nodes_++;
+  nodes[(size_t)id] = Node{-1, 0.0, lo, hi, -1, -1};
   // bounding box of the node's points; split the widest dimension at the median
   int best = 0;
   double bw = -1;
@@ -65,8 +78,16 @@ int64_t KDTree::build_rec(int64_t lo, int64_t hi) {
     return va < vb || (va == vb && a < b);
   });
   double split = pts[perm[mid] * nd + best];
-  int64_t l = build_rec(lo, mid);
-  int64_t r = build_rec(mid, hi);
+  int64_t l, r;
+  if (hi - lo > 16384) {
+#pragma omp task shared(l)
+    l = build_rec(lo, mid);
+    r = build_rec(mid, hi);
+#pragma omp taskwait
+  } else {
+    l = build_rec(lo, mid);
+    r = build_rec(mid, hi);
+  }
   nodes[id].dim = best;
   nodes[id].split = split;
   nodes[id].left = l;
@@ -502,6 +523,7 @@ static void simplex_centers_normals(const ibx_stl& s, std::vector<double>& cente
   normals.assign((size_t)ns * nd, 0.0);
   auto run = [&](auto tag) {
     using T = decltype(tag);
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < ns; ++i) {
       T p[9];
       for (int v = 0; v < nd; ++v)
@@ -551,28 +573,66 @@ static std::shared_ptr<ibx_stl> merge_points_impl(const std::vector<const ibx_st
       return (size_t)h;
     }
   };
-  std::unordered_map<Key, int64_t, KeyHash> tag2ind;
-  std::vector<int64_t> simp;
-  for (const ibx_stl* s : in) {
-    int64_t np = s->npoints();
-    std::vector<int64_t> newidx(np);
+  // Points are numbered globally over the inputs; the representative of a point is the FIRST point carrying its tag,
+  // and kept points are numbered in order of first appearance -- the result of the reference's sequential loop.  The
+  // tags are computed in parallel, the points split into buckets by tag hash (lists in ascending point order), and
+  // every bucket resolved by its own hash map in parallel.
+  std::vector<int64_t> off(in.size() + 1, 0);
+  for (size_t k = 0; k < in.size(); ++k) off[k + 1] = off[k] + in[k]->npoints();
+  const int64_t NP = off.back();
+  std::vector<Key> keys((size_t)NP);
+  constexpr int NBUCKET = 1024;
+  std::vector<uint16_t> bucket((size_t)NP);
+  for (size_t k = 0; k < in.size(); ++k) {
+    const ibx_stl* s = in[k];
+    const int64_t np = s->npoints();
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < np; ++i) {
-      Key k{{0, 0, 0}};
+      Key key{{0, 0, 0}};
       for (int d = 0; d < nd; ++d) {
         double q = (s->f32 && tol_f32) ? (double)((float)s->points[i * nd + d] / (float)tol) : s->points[i * nd + d] / tol;
-        k.v[d] = (int64_t)std::nearbyint(q);
+        key.v[d] = (int64_t)std::nearbyint(q);
       }
-      auto it = tag2ind.find(k);
-      if (it == tag2ind.end()) {
-        int64_t id = out->npoints();
-        tag2ind.emplace(k, id);
-        for (int d = 0; d < nd; ++d) out->points.push_back(s->points[i * nd + d]);
-        newidx[i] = id;
-      } else {
-        newidx[i] = it->second;
-      }
+      keys[(size_t)(off[k] + i)] = key;
+      bucket[(size_t)(off[k] + i)] = (uint16_t)(KeyHash()(key) % NBUCKET);
     }
-    for (int64_t v : s->simplices) simp.push_back(newidx[v]);
+  }
+  std::vector<int64_t> bptr(NBUCKET + 1, 0);
+  for (int64_t i = 0; i < NP; ++i) ++bptr[bucket[(size_t)i] + 1];
+  for (int q = 0; q < NBUCKET; ++q) bptr[q + 1] += bptr[q];
+  std::vector<int64_t> blist((size_t)NP);
+  {
+    std::vector<int64_t> fill(bptr.begin(), bptr.end() - 1);
+    for (int64_t i = 0; i < NP; ++i) blist[(size_t)fill[bucket[(size_t)i]]++] = i;
+  }
+  std::vector<int64_t> rep((size_t)NP);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int q = 0; q < NBUCKET; ++q) {
+    std::unordered_map<Key, int64_t, KeyHash> first;
+    first.reserve((size_t)(bptr[q + 1] - bptr[q]));
+    for (int64_t j = bptr[q]; j < bptr[q + 1]; ++j) {
+      const int64_t i = blist[(size_t)j];
+      rep[(size_t)i] = first.emplace(keys[(size_t)i], i).first->second;
+    }
+  }
+  std::vector<int64_t> newid((size_t)NP);   // valid at representatives
+  int64_t nkept = 0;
+  for (int64_t i = 0; i < NP; ++i)
+    if (rep[(size_t)i] == i) newid[(size_t)i] = nkept++;
+  out->points.resize((size_t)nkept * nd);
+  std::vector<int64_t> simp;
+  for (size_t k = 0; k < in.size(); ++k) {
+    const ibx_stl* s = in[k];
+    const int64_t np = s->npoints();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < np; ++i)
+      if (rep[(size_t)(off[k] + i)] == off[k] + i)
+        for (int d = 0; d < nd; ++d) out->points[(size_t)(newid[(size_t)(off[k] + i)] * nd + d)] = s->points[i * nd + d];
+    const size_t base = simp.size();
+    simp.resize(base + s->simplices.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < (int64_t)s->simplices.size(); ++j)
+      simp[base + (size_t)j] = newid[(size_t)rep[(size_t)(off[k] + s->simplices[(size_t)j])]];
   }
   int64_t ns = (int64_t)simp.size() / nd;
   for (int64_t i = 0; i < ns; ++i) {
@@ -648,16 +708,27 @@ std::shared_ptr<ibx_stl> refine_to_length_impl(const ibx_stl& s, Num h, double t
   double gm1 = growth_ratio - 1.0;
   auto run = [&](auto tag) {
     using T = decltype(tag);
-    std::vector<T> out;
-    for (int64_t i = 0; i < s.nsimp(); ++i) {
-      std::vector<T> simp((size_t)nd * nd);
-      for (int v = 0; v < nd; ++v)
-        for (int d = 0; d < nd; ++d) simp[v * nd + d] = (T)s.points[s.simplices[i * nd + v] * nd + d];
-      refine_simplex<T>(std::move(simp), nd, h, gm1, nreg, regs, out);
+    // every input simplex refines on its own: chunks in parallel, outputs concatenated in input order
+    const int64_t ns = s.nsimp(), CH = 64, nch = (ns + CH - 1) / CH;
+    std::vector<std::vector<T>> outs((size_t)nch);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c = 0; c < nch; ++c) {
+      std::vector<T>& out = outs[(size_t)c];
+      for (int64_t i = c * CH; i < std::min(ns, (c + 1) * CH); ++i) {
+        std::vector<T> simp((size_t)nd * nd);
+        for (int v = 0; v < nd; ++v)
+          for (int d = 0; d < nd; ++d) simp[v * nd + d] = (T)s.points[s.simplices[i * nd + v] * nd + d];
+        refine_simplex<T>(std::move(simp), nd, h, gm1, nreg, regs, out);
+      }
     }
-    tmp.points.assign(out.begin(), out.end());
+    size_t total = 0;
+    for (auto& o : outs) total += o.size();
+    tmp.points.reserve(total);
+    for (auto& o : outs) tmp.points.insert(tmp.points.end(), o.begin(), o.end());
   };
+  double t0 = omp_get_wtime();
   if (s.f32) run(float{}); else run(double{});
+  if (getenv("IBX_BUILD_VERBOSE")) fprintf(stderr, "[ibx mesh ]   refine loop %.2f s, %lld points\n", omp_get_wtime() - t0, (long long)tmp.npoints());
   int64_t np = tmp.npoints();
   tmp.simplices.resize(np);
   std::iota(tmp.simplices.begin(), tmp.simplices.end(), (int64_t)0);
@@ -673,6 +744,7 @@ std::shared_ptr<ibx_dfield> make_dfield(std::shared_ptr<ibx_stl> stl) {
   {
     const int nd = stl->nd;
     double r2 = 0;
+#pragma omp parallel for schedule(static) reduction(max : r2)
     for (int64_t i = 0; i < stl->nsimp(); ++i)
       for (int v = 0; v < nd; ++v) {
         double a = 0;

@@ -74,6 +74,7 @@ struct KDTree {
     return acc;
   }
  private:
+  int64_t n_nodes_ = 0;
   int64_t build_rec(int64_t lo, int64_t hi);
 };
 

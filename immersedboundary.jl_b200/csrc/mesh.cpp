@@ -2,6 +2,8 @@
 // Mirrors src/mesher.jl:811-1112 of the reference (refine_octree, refine_orderly, Mesh, get_cells).
 #include "ibx_internal.h"
 #include <cstdio>
+#include <cstdlib>
+#include <omp.h>
 
 #include <numeric>
 
@@ -26,22 +28,33 @@ struct Criterion {
   Num h;
 };
 
-// refine_octree (src/mesher.jl:811-862): depth-first, children in Iterators.product order (first dim fastest)
-static void refine_octree(const std::vector<Criterion>& crit, int nd, const float* origin, const float* widths,
-                          double gm1, std::vector<float>& out_o, std::vector<float>& out_w) {
-  struct Item {
-    float o[3], w[3];
-    std::vector<int> active;  // indices into crit
-  };
-  std::vector<Item> stack;
-  Item root;
-  for (int d = 0; d < nd; ++d) { root.o[d] = origin[d]; root.w[d] = widths[d]; }
-  root.active.resize(crit.size());
-  std::iota(root.active.begin(), root.active.end(), 0);
+// refine_octree (src/mesher.jl:811-862): depth-first, children in Iterators.product order (first dim fastest).
+// The subtrees below depth PAR_DEPTH are independent: the top of the tree is walked serially, every node met at that
+// depth becomes a task, the tasks run in parallel and their leaves are spliced back in depth-first order -- the block
+// list is the serial one.
+namespace {
+struct OctItem {
+  float o[3], w[3];
+  int depth;
+  std::vector<int> active;  // indices into crit
+};
+struct OctOut {
+  std::vector<float> o, w;
+  std::vector<OctItem> tasks;                // nodes left unexpanded (serial top only)
+  std::vector<std::pair<int64_t, int>> at;   // (number of leaves emitted before the task, task id)
+};
+
+void octree_dfs(const std::vector<Criterion>& crit, int nd, double gm1, OctItem root, int stop_depth, OctOut& out) {
+  std::vector<OctItem> stack;
   stack.push_back(std::move(root));
   while (!stack.empty()) {
-    Item it = std::move(stack.back());
+    OctItem it = std::move(stack.back());
     stack.pop_back();
+    if (stop_depth >= 0 && it.depth == stop_depth) {
+      out.at.emplace_back((int64_t)out.o.size() / nd, (int)out.tasks.size());
+      out.tasks.push_back(std::move(it));
+      continue;
+    }
     float L = it.w[0], wmin = it.w[0];
     double ss = 0;
     for (int d = 0; d < nd; ++d) {
@@ -59,7 +72,7 @@ static void refine_octree(const std::vector<Criterion>& crit, int nd, const floa
       if (lmax.v < (double)L) active.push_back(ci);
     }
     if (active.empty()) {
-      for (int d = 0; d < nd; ++d) { out_o.push_back(it.o[d]); out_w.push_back(it.w[d]); }
+      for (int d = 0; d < nd; ++d) { out.o.push_back(it.o[d]); out.w.push_back(it.w[d]); }
       continue;
     }
     int split[3] = {1, 1, 1};
@@ -79,12 +92,52 @@ static void refine_octree(const std::vector<Criterion>& crit, int nd, const floa
     for (int idx = total - 1; idx >= 0; --idx) {
       int i0 = idx % split[0], i1 = (idx / split[0]) % split[1], i2 = idx / (split[0] * split[1]);
       int ii[3] = {i0, i1, i2};
-      Item ch;
+      OctItem ch;
       for (int d = 0; d < nd; ++d) { ch.o[d] = axes[d][ii[d]]; ch.w[d] = nw[d]; }
+      ch.depth = it.depth + 1;
       ch.active = active;
       stack.push_back(std::move(ch));
     }
   }
+}
+}  // namespace
+
+static void refine_octree(const std::vector<Criterion>& crit, int nd, const float* origin, const float* widths,
+                          double gm1, std::vector<float>& out_o, std::vector<float>& out_w) {
+  constexpr int PAR_DEPTH = 5;
+  OctItem root;
+  for (int d = 0; d < nd; ++d) { root.o[d] = origin[d]; root.w[d] = widths[d]; }
+  root.depth = 0;
+  root.active.resize(crit.size());
+  std::iota(root.active.begin(), root.active.end(), 0);
+  OctOut top;
+  octree_dfs(crit, nd, gm1, std::move(root), PAR_DEPTH, top);
+  const int nt = (int)top.tasks.size();
+  std::vector<OctOut> sub((size_t)nt);
+  std::string err;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < nt; ++t) {
+    try {
+      octree_dfs(crit, nd, gm1, std::move(top.tasks[t]), -1, sub[(size_t)t]);
+    } catch (const std::exception& e) {
+#pragma omp critical
+      err = e.what();
+    }
+  }
+  if (!err.empty()) throw std::runtime_error(err);
+  int64_t pos = 0;   // leaves of the serial top copied so far
+  auto copy_top = [&](int64_t upto) {
+    out_o.insert(out_o.end(), top.o.begin() + pos * nd, top.o.begin() + upto * nd);
+    out_w.insert(out_w.end(), top.w.begin() + pos * nd, top.w.begin() + upto * nd);
+    pos = upto;
+  };
+  for (const auto& a : top.at) {
+    copy_top(a.first);
+    const OctOut& s = sub[(size_t)a.second];
+    out_o.insert(out_o.end(), s.o.begin(), s.o.end());
+    out_w.insert(out_w.end(), s.w.begin(), s.w.end());
+  }
+  copy_top((int64_t)top.o.size() / nd);
 }
 
 // get_cells, margin = 0 (src/mesher.jl:1064-1112) for ONE block: cpb x nd centres / widths, first dim fastest.  The
@@ -151,6 +204,12 @@ int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf,
   m->nd = nd;
   m->block_size = block_size;
   for (int d = 0; d < nd; ++d) { m->origin[d] = origin[d]; m->widths[d] = widths[d]; }
+  const bool verbose = getenv("IBX_BUILD_VERBOSE") != nullptr;   // phase times, like the Domain build
+  double t_phase = omp_get_wtime();
+  auto phase = [&](const char* what) {
+    if (verbose) fprintf(stderr, "[ibx mesh ] %-28s %8.2f s\n", what, omp_get_wtime() - t_phase);
+    t_phase = omp_get_wtime();
+  };
   // refine_orderly (src/mesher.jl:878-918): surfaces by increasing h; every refined surface becomes a
   // refinement region (at h * ratio, ratio = 0.5f0) for the ones that follow
   const float ratio = 0.5f;
@@ -179,7 +238,9 @@ int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf,
     if (sf.stl) {
       auto stl = refine_to_length_impl(*lookup_stl(sf.stl), h, tolerance, tol_is_f32 != 0, growth_ratio,
                                        (int)regs.size(), regs.data());
+      phase("refine_to_length");
       df = make_dfield(stl);
+      phase("distance field");
     } else {
       IBX_REQUIRE(nd == 3, "analytic sphere surfaces are 3-D only");
       df = std::make_shared<ibx_dfield>();
@@ -219,6 +280,7 @@ int ibx_mesh_create(int nd, const float* origin, const float* widths, int nsurf,
     crit.push_back(c);
   }
   refine_octree(crit, nd, m->origin, m->widths, growth_ratio - 1.0, m->block_origins, m->block_widths);
+  phase("octree");
   g_mesh[m.get()] = m;
   *out = m.get();
   return IBX_OK;
