@@ -481,11 +481,17 @@ void ibx_dfield::projection(const double* x, bool xf32, double R, double* out) c
     for (int k = 0; k < nd; ++k) { double t = centers[cand[q] * nd + k] - x[k]; a += t * t; }
     byd[q] = {std::sqrt(a), cand[q]};
   }
-  std::sort(byd.begin(), byd.end());
+  // few candidates (a finely triangulated surface: nearly all of them end up evaluated): ascending index order, no sort;
+  // the `dd == dmin && s < imin` rule below makes the winner independent of the visiting order either way
+  const bool sorted = cand.size() > 192;
+  if (sorted) std::sort(byd.begin(), byd.end());
   double dmin = INFINITY, pmin[3] = {0, 0, 0};
   int64_t imin = -1;
   for (const auto& c : byd) {
-    if (c.first > (std::min(dmin, d) + rmax) * margin + 1e-30) break;
+    if (c.first > (std::min(dmin, d) + rmax) * margin + 1e-30) {
+      if (sorted) break;
+      continue;
+    }
     const int64_t s = c.second;
     double pr[3], dd;
     if (f) {
