@@ -3,16 +3,18 @@ with local time steps around `ibx_step_euler`, ghost cells frozen between residu
 libibx kernel, no host round trip per step) next to the compiled CPU restatement of the reference path running the SAME
 driver (`tools/c3_converge.py`, oracle/cpu_ref.c on the tables of the product's host builder).
 
-1. a short march through the start-up transient, oracle run live here: Cl / Cd within 2e-5, state within 1e-4 of its
-   per-variable scale on average and 1e-2 at worst;
+1. a short march through the start-up transient, oracle run live here;
 2. the long march to the steady state against `tests/golden/rae2822_converged.npz` (written by `tools/c3_converge.py
-   --save`, command in the fixture's `command` field): lift and drag coefficients within 1e-4 -- the north-star figure for
-   Cl / Cd.
+   --save`, command in the fixture's `command` field): 120 000 steps, 360 000 ghost updates + residuals + updates.
 
-Why the state tolerance is loose while Cl / Cd is tight: the impulsive start sends sharp fronts through the field (the
-expansion over the upper surface, then the starting vortex down the wake).  Perturbing the ORACLE's residual by 1e-7
-relative noise per stage (one float32 ulp; the 2-D tile kernels agree with the oracle to 2e-6 of scale, not to the bit)
-moves the state by up to 1e-3 of scale at those fronts after 150 steps, yet Cl and Cd by 3e-6 at most."""
+In both the device state must EQUAL the oracle's bit for bit (ghost update, residual, CFL term and the update kernel
+round identically, so the two marches never separate), and lift / drag must agree within 1e-4 -- the north-star figure
+for Cl / Cd; they differ by the summation order of the surface integral only (measured: 5e-7 / 2e-8).
+
+Why equality and not a tolerance: the impulsive start sends sharp fronts through the field (the expansion over the
+upper surface, then the starting vortex down the wake).  Perturbing the ORACLE's residual by 1e-7 relative noise per
+stage -- one float32 ulp -- moves the state by up to 1e-3 of scale at those fronts after 150 steps (Cl / Cd by 3e-6):
+a state tolerance that is both safe and meaningful does not exist for this march."""
 import json
 import os
 import time
@@ -77,7 +79,7 @@ def test_transient_march_matches_cpu_reference(get_case, ib, oracle):
             Qo = np.asfortranarray(Qs + (F32(a) * CFL / cf)[:, None] * R * live[:, None])
     assert np.isfinite(Qg).all() and np.abs(Qg - Q0).max() > 0
     err = (np.abs(Qg - Qo) / np.abs(Qo).max(axis=0)).max(axis=1)
-    assert err.mean() < 1e-4 and err.max() < 1e-2, (err.mean(), err.max())
+    assert np.array_equal(Qg, Qo), f"{(err > 0).sum()} of {N} cells differ, max {err.max():.3e} of scale"
     (cl, cd), (clo, cdo) = (_lift_drag(ib, fl, dom, ib.DeviceArray.from_host(np.asfortranarray(q)), Pinf, 0.73, 2.31) for q in (Qg, Qo))
     assert abs(cl - clo) < 2e-5 and abs(cd - cdo) < 2e-5, (cl, clo, cd, cdo)
     assert abs(cl) > 0.1                                           # lift has built up
@@ -111,6 +113,6 @@ def test_converged_lift_and_drag(get_case, ib):
     assert abs(cl - float(g["cl"])) < 1e-4 and abs(cd - float(g["cd"])) < 1e-4, (cl, float(g["cl"]), cd, float(g["cd"]), hist[-3:])
     Qg, Qo = Q.to_host(), g["Q"]
     err = (np.abs(Qg - Qo) / np.abs(Qo).max(axis=0)).max(axis=1)
-    assert np.isfinite(Qg).all() and err.mean() < 1e-4, (err.mean(), err.max())
+    assert np.isfinite(Qg).all() and np.array_equal(Qg, Qo), f"{(err > 0).sum()} cells differ, max {err.max():.3e} of scale"
     # steady: over the last 5 % of the march lift and drag move no more than they did in the oracle's march
     assert abs(hist[-1][1] - hist[-2][1]) < 2 * float(g["cl_drift"]) + 1e-5 and abs(hist[-1][2] - hist[-2][2]) < 2 * float(g["cd_drift"]) + 1e-5, hist[-3:]
