@@ -352,7 +352,7 @@ int ibx_mesh_load(const char* path, ibx_mesh** out) {
     int32_t nd, bs, ns;
     get(f, nd);
     get(f, bs);
-    if (nd < 2 || nd > 3 || bs < 1) throw std::runtime_error("corrupt mesh file");
+    if (nd < 2 || nd > 3 || bs < 1 || bs > 64) throw std::runtime_error("corrupt mesh file");
     m->nd = nd;
     m->block_size = bs;
     for (int d = 0; d < 3; ++d) { get(f, m->origin[d]); get(f, m->widths[d]); }
