@@ -553,6 +553,79 @@ int ibx_step_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, 
   return step_euler_impl(c, d, f, flux_kind, nbc, bcs, 0, Qh, Rh, cflh);
 }
 
+// Pseudo-time march with local time steps, whole loop on the device (the driver a user writes around `FAS!` or by hand,
+// test/advection.jl:28-46): per step  ghost updates in place;  Q0 = Q;  for every stage coefficient a:
+// ibx_step_euler (ghost updates + residual), Q = Q0 + ((a CFL / cfl) R) live.  On small meshes the loop is launch-bound
+// (C3: ~40 launches of a few microseconds per stage), so one step is captured into a CUDA graph after a warm-up step
+// has sized every scratch array, and replayed; the kernels and their order are those of the plain loop: same bits.
+int ibx_march_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs, ibx_array Qh,
+                    ibx_array liveh, int64_t n_steps, float CFL, int nstages, const float* alphas, int use_graph, int* graph_used) {
+  CHECK_CTX(c);
+  GET_DOM(D, d);
+  GET_ARR(Q, Qh);
+  if (graph_used) *graph_used = 0;
+  if (nstages < 1 || nstages > 8 || !alphas) return fail(IBX_ERR_ARG, "ibx_march_euler: 1 .. 8 stage coefficients");
+  if (n_steps < 0) return fail(IBX_ERR_ARG, "ibx_march_euler: negative step count");
+  if (D.shard.active && D.shard.nranks > 1) return fail(IBX_ERR_UNSUPPORTED, "ibx_march_euler: whole domains only (use ibx_step_euler_sharded in a host loop)");
+  const int nv = D.nd + 2;
+  SHAPE(Q.rows == D.ncells && Q.cols == nv, "Q must be ncells x (nd + 2)");
+  if (n_steps == 0) return IBX_OK;
+  int rc;
+  ibx_array Q0h = 0, Rh = 0, cfh = 0;
+  if ((rc = ibx_array_alloc(c, Q.rows, nv, &Q0h)) || (rc = ibx_array_alloc(c, Q.rows, nv, &Rh)) || (rc = ibx_array_alloc(c, Q.rows, 1, &cfh))) {
+    if (Q0h) ibx_array_free(c, Q0h);
+    if (Rh) ibx_array_free(c, Rh);
+    return rc;
+  }
+  auto one_step = [&]() -> int {
+    int r;
+    for (int k = 0; k < nbc; ++k)
+      if ((r = ibx_ghost_update_euler(c, d, bcs[k].boundary, f, bcs[k].Pinf, bcs[k].n_pinf, bcs[k].normal_flow, Qh))) return r;
+    if ((r = ibx_array_copy(c, Q0h, Qh))) return r;
+    for (int s = 0; s < nstages; ++s) {
+      if ((r = step_euler_impl(c, d, f, flux_kind, nbc, bcs, 0, Qh, Rh, cfh))) return r;
+      if ((r = ibx_local_step_update(c, Q0h, Rh, cfh, liveh, alphas[s] * CFL, Qh))) return r;
+    }
+    return IBX_OK;
+  };
+  auto done = [&](int code) {
+    ibx_array_free(c, Q0h);
+    ibx_array_free(c, Rh);
+    ibx_array_free(c, cfh);
+    return code;
+  };
+  int64_t left = n_steps;
+  if ((rc = one_step())) return done(rc);        // also the warm-up that sizes the scratch arrays and sets kernel attributes
+  --left;
+  if (use_graph && left > 0) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const bool was_poisoned = c->poisoned;   // an error raised while capturing is not a sticky device error
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+      const int rcap = one_step();
+      const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+      if (rcap == IBX_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        for (; left > 0; --left)
+          if (cudaGraphLaunch(exec, c->stream) != cudaSuccess) break;
+        if (graph_used) *graph_used = left == 0;
+      }
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+      if (left > 0) {
+        cudaGetLastError();
+        c->poisoned = was_poisoned;
+        return done(fail(IBX_ERR_CUDA, "ibx_march_euler: CUDA graph capture / replay of one step failed (call again with use_graph = 0)"));
+      }
+    } else {
+      cudaGetLastError();
+      return done(fail(IBX_ERR_CUDA, "ibx_march_euler: cudaStreamBeginCapture failed (call again with use_graph = 0)"));
+    }
+  }
+  for (; left > 0; --left)
+    if ((rc = one_step())) return done(rc);
+  return done(IBX_OK);
+}
+
 int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
                            int exchange_between_families, ibx_array Qh, ibx_array Rh, ibx_array cflh) {
   if (c) {

@@ -601,17 +601,17 @@ local_step_update!(Q::IBXArray, Q0::IBXArray, R::IBXArray, cfl::IBXArray, alpha:
 multistage coefficient `a`: `step_euler!` and `Q = Q0 + a CFL R / cfl * live`.  `live` (0/1 per cell) freezes the ghost cells
 between residual evaluations (they only take boundary values)."""
 function march_euler!(dom::Domain, fluid::Fluid, bcs::Vector{Pair{String, FlowBC}}, Q::IBXArray, n_steps::Int;
-                      CFL::Real = 0.8f0, stages = (0.1481f0, 0.4f0, 1.0f0), live::Union{Nothing, IBXArray} = nothing, flux_kind::Int = 0)
-    R = similar(Q); cfl = IBXArray{1}((size(Q, 1),)); Q0 = similar(Q)
-    for _ = 1:n_steps
-        for (n, bc) in bcs
-            ghost_update_euler!(dom, fluid, n, bc, Q)
-        end
-        copyto!(Q0, Q)
-        for a in stages
-            step_euler!(dom, fluid, bcs, Q, R, cfl; flux_kind = flux_kind)
-            local_step_update!(Q, Q0, R, cfl, Float32(a) * Float32(CFL); mask = live)
-        end
+                      CFL::Real = 0.8f0, stages = (0.1481f0, 0.4f0, 1.0f0), live::Union{Nothing, IBXArray} = nothing, flux_kind::Int = 0,
+                      graph::Bool = true)
+    # the whole loop runs inside the library (`ibx_march_euler`); with `graph` one step is replayed from a CUDA graph
+    specs = [BCSpec(dom, n, bc) for (n, bc) in bcs]
+    al = Float32[stages...]
+    used = Ref{Cint}(0)
+    GC.@preserve specs al begin
+        check(ccall((:ibx_march_euler, libibx), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Fluid, Cint, Cint, Ptr{BCSpec}, Int64, Int64, Int64, Cfloat, Cint, Ptr{Cfloat}, Cint, Ref{Cint}),
+                    context(), dom.h, fluid, flux_kind, length(specs), specs, Q.h, isnothing(live) ? 0 : live.h, n_steps, Float32(CFL),
+                    length(al), al, graph, used))
     end
     Q
 end

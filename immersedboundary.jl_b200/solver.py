@@ -51,7 +51,7 @@ def local_step_update(Q0, R, cfl, alpha, Q, mask=None):
     return Q
 
 
-def march_euler(dom, fluid, bcs, Q, n_steps, CFL=0.8, stages=3, live=None, flux="hll", monitor=None, every=0):
+def march_euler(dom, fluid, bcs, Q, n_steps, CFL=0.8, stages=3, live=None, flux="hll", monitor=None, every=0, native=True, graph=True):
     """Pseudo-time march of the Euler residual with local time steps, the driver loop the reference leaves to its users
     (``test/advection.jl:28-46`` applies the BCs to the marched state and advances it by ``R * CFL / cfl``; ``FAS!``
     with ``f(l, Q) = (R .* CFL ./ cfl, 1)``, ``src/solver.jl:78-82``, is the single-stage case).
@@ -60,10 +60,24 @@ def march_euler(dom, fluid, bcs, Q, n_steps, CFL=0.8, stages=3, live=None, flux=
     ``step_euler`` (ghost update + residual) and ``Q = Q0 + a CFL R / cfl * live``.  ``live`` (N x 1 of 0/1) freezes
     cells between residual evaluations -- the ghost cells, which only ever take boundary values: a ghost cell advanced by
     its own residual drifts, and so does every image point that interpolates from it.  Everything runs on the device;
-    ``monitor(step, Q, R, cfl)`` is called every ``every`` steps with the arrays of the last stage."""
-    from . import cfd
+    ``monitor(step, Q, R, cfl)`` is called every ``every`` steps with the arrays of the last stage.
+
+    Without a monitor the whole loop runs inside the library (``ibx_march_euler``, ``native=True``): one step is captured
+    into a CUDA graph and replayed (``graph=True``) -- on a small mesh the loop is launch-bound -- with the same kernels
+    in the same order, hence the same bits as the host loop below.  ``march_euler.last_graph_used`` tells whether the
+    graph path ran."""
+    from . import _lib, cfd
 
     alphas = RK_STAGES[stages] if isinstance(stages, int) else tuple(stages)
+    if native and monitor is None and not getattr(dom, "shard_info", None):
+        dom.upload()
+        specs = (_lib.BCSpec * max(len(bcs), 1))(*[bc.spec(dom.boundary_index[name]) for name, bc in bcs])
+        al = np.ascontiguousarray(alphas, dtype=F32)
+        used = C.c_int(0)
+        call("ibx_march_euler", context(), dom._h, fluid.c, 0 if flux == "hll" else 1, len(bcs), specs, Q.h, 0 if live is None else live.h,
+             int(n_steps), float(F32(CFL)), len(al), ptr(al), int(bool(graph)), C.byref(used))
+        march_euler.last_graph_used = bool(used.value)
+        return Q
     R = DeviceArray(Q.rows, Q.cols, False)
     cf = DeviceArray(Q.rows, 1, True)
     Q0 = Q.like()

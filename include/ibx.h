@@ -431,6 +431,15 @@ int ibx_shard_phase_info(const ibx_domain* local, int64_t* n_flux_early, int64_t
 int ibx_step_euler_sharded(ibx_ctx* c, const ibx_domain* local, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs,
                            int exchange_between_families, ibx_array Q, ibx_array R, ibx_array cfl);
 
+/* Pseudo-time march of the Euler residual with local time steps, n_steps steps entirely on the device (the loop a user
+ * writes around `FAS!`'s f(l, Q) = (R .* CFL ./ cfl, 1), src/solver.jl:78-82, or by hand as in test/advection.jl:28-46).
+ * Per step: ghost updates of `bcs` on Q in place; Q0 = Q; for each of the nstages coefficients a: ibx_step_euler, then
+ * Q = Q0 + ((a CFL / cfl) R) live  (live = 0: every cell advances; else an ncells x 1 array of 0 / 1 -- pass 0 on the ghost
+ * cells, which only take boundary values).  use_graph != 0 replays one captured step as a CUDA graph (launch-bound small
+ * meshes); *graph_used reports it.  Whole domains only. */
+int ibx_march_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, int nbc, const ibx_bc_spec* bcs, ibx_array Q,
+                    ibx_array live, int64_t n_steps, float CFL, int nstages, const float* alphas, int use_graph, int* graph_used);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,8 +61,15 @@ def test_transient_march_matches_cpu_reference(get_case, ib, oracle):
     dom = get_case("rae2822", 10_000, upload=True).dom
     fl, Pinf, wall, bcs, Q0, live = _setup(ib, dom, 0.73, 2.31)
     Q = ib.DeviceArray.from_host(Q0)
-    ib.march_euler(dom, fl, bcs, Q, STEPS, CFL=CFL, stages=STAGES, live=ib.DeviceArray.from_host(live))
+    dlive = ib.DeviceArray.from_host(live)
+    ib.march_euler(dom, fl, bcs, Q, STEPS, CFL=CFL, stages=STAGES, live=dlive, native=False)      # host loop over the C ABI
     Qg = Q.to_host()
+    # ---- the loop inside the library (ibx_march_euler), plain and replayed from a CUDA graph: same kernels, same bits
+    for graph in (False, True):
+        Qn = ib.DeviceArray.from_host(Q0)
+        ib.march_euler(dom, fl, bcs, Qn, STEPS, CFL=CFL, stages=STAGES, live=dlive, native=True, graph=graph)
+        assert ib.march_euler.last_graph_used == graph
+        assert np.array_equal(Qn.to_host(), Qg), f"native march (graph={graph}) differs from the host loop"
     # ---- the same driver around the CPU restatement (tools/c3_converge.py)
     ref = cpu_ref.CpuRef.from_builder(dom)
     ofl = cfd.Fluid()
@@ -97,15 +104,23 @@ def test_converged_lift_and_drag(get_case, ib):
         hist.append((it,) + _lift_drag(ib, fl, dom, Q, Pinf, mach, alpha))
 
     t0 = time.time()
-    ib.march_euler(dom, fl, bcs, Q, steps, CFL=cfl, stages=stages, live=ib.DeviceArray.from_host(live), monitor=monitor,
-                   every=max(steps // 20, 1))
+    dlive = ib.DeviceArray.from_host(live)
+    ib.march_euler(dom, fl, bcs, Q, steps, CFL=cfl, stages=stages, live=dlive, monitor=monitor, every=max(steps // 20, 1))
     cl, cd = _lift_drag(ib, fl, dom, Q, Pinf, mach, alpha)
     seconds = time.time() - t0
+    # the same march inside the library, one step captured into a CUDA graph and replayed
+    Qn = ib.DeviceArray.from_host(Q0)
+    t1 = time.time()
+    ib.march_euler(dom, fl, bcs, Qn, steps, CFL=cfl, stages=stages, live=dlive)
+    Qn_host = Qn.to_host()
+    seconds_graph = time.time() - t1
+    assert ib.march_euler.last_graph_used
     if os.environ.get("IBX_C3_OUT"):                               # evidence file for profiles/
         err = (np.abs(Q.to_host() - g["Q"]) / np.abs(g["Q"]).max(axis=0)).max(axis=1)
         with open(os.environ["IBX_C3_OUT"], "w") as f:
             json.dump({"case": "rae2822 M=0.73 alpha=2.31 Euler", "cells": len(dom), "steps": steps, "stages": stages, "cfl": float(cfl),
                        "seconds": round(seconds, 2), "residual_evaluations_per_s": round(steps * stages / seconds, 1),
+                       "seconds_cuda_graph": round(seconds_graph, 2), "graph_state_equal": bool(np.array_equal(Qn_host, Q.to_host())),
                        "gpu": {"cl": cl, "cd": cd}, "oracle": {"cl": float(g["cl"]), "cd": float(g["cd"])},
                        "abs_diff": {"cl": abs(cl - float(g["cl"])), "cd": abs(cd - float(g["cd"]))},
                        "state_err_of_scale": {"mean": float(err.mean()), "max": float(err.max())}, "history_step_cl_cd": hist}, f, indent=1)
@@ -114,5 +129,6 @@ def test_converged_lift_and_drag(get_case, ib):
     Qg, Qo = Q.to_host(), g["Q"]
     err = (np.abs(Qg - Qo) / np.abs(Qo).max(axis=0)).max(axis=1)
     assert np.isfinite(Qg).all() and np.array_equal(Qg, Qo), f"{(err > 0).sum()} cells differ, max {err.max():.3e} of scale"
+    assert np.array_equal(Qn_host, Qo), "the graph-replayed march differs from the oracle's"
     # steady: over the last 5 % of the march lift and drag move no more than they did in the oracle's march
     assert abs(hist[-1][1] - hist[-2][1]) < 2 * float(g["cl_drift"]) + 1e-5 and abs(hist[-1][2] - hist[-2][2]) < 2 * float(g["cd_drift"]) + 1e-5, hist[-3:]
