@@ -360,7 +360,14 @@ int ibx_get_option(ibx_ctx* c, const char* name, int* value);
 /* Linear advection residual of test/advection.jl:67-83 on the whole domain:
  * ud = -sum_dim GG(upwind MUSCL flux), spec = max_dim UGG(at_faces(C_dim)). u, ud, spec: N; C: N x nd. */
 int ibx_residual_advection(ibx_ctx* c, const ibx_domain* d, ibx_array u, ibx_array C, ibx_array ud, ibx_array spec);
-/* Canonical Euler residual: Q -> (R, cfl).  flux_kind 0 = HLL, 1 = sensor-Rusanov. */
+/* Canonical Euler residual: Q -> (R, cfl).  flux_kind 0 = HLL, 1 = sensor-Rusanov.
+ * Domain of the default path ("path" = 0 on 3-D, block size 8): its divisions, square roots and the Float64 reciprocal
+ * are the straight-line sequences ptxas emits when its own range check passes, without the check.  They are correctly
+ * rounded for operands and results between 2^-100 and 2^100 in magnitude -- pressures, R T, gamma R T (the temperature
+ * is clamped at 10 K first, src/cfd.jl:140) and wave-speed differences of any physical flow; a zero wave-speed
+ * difference gives NaN like the reference's 0 / 0.  A state that has diverged beyond that range gets unspecified finite
+ * values or NaN instead of the IEEE result: detect it with ibx_reduce (max / min / max|.| propagate NaN) or re-run the
+ * step with "path" = 1 or 2, whose kernels keep the guarded library forms. */
 int ibx_residual_euler(ibx_ctx* c, const ibx_domain* d, ibx_fluid f, int flux_kind, ibx_array Q, ibx_array R,
                        ibx_array cfl);
 /* Configuration C5 -- canonical RANS residual (ours: the reference ships the pieces, not a composition; oracle/euler.py
