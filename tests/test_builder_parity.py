@@ -133,3 +133,65 @@ def test_block_face_table_consistent_with_faces(get_case):
         e2 = bf[bn, 2 * dim]
         assert e2[0] in (1, 2, 3) and bo in e2[1:5]
         assert {e[0], e2[0]} in ({1}, {2, 3})
+
+
+class _AdHoc:
+    """A one-off configuration built through the product and through the oracle (same shape as conftest.Case)."""
+
+    def __init__(self, ib, oracle, origin, widths, surfaces, regions, fams, mps=100_000, block_size=8):
+        M, OM = ib, oracle.mesher
+        self.msh = M.Mesh(origin, widths, *surfaces(M), refinement_regions=regions(M), block_size=block_size)
+        self.omsh = OM.Mesh(origin, widths, *surfaces(OM), refinement_regions=regions(OM), block_size=block_size)
+        self.dom = ib.Domain(self.msh, max_partition_size=mps, hypercube_families=fams, upload=False)
+        self.odom = oracle.domain.Domain(self.omsh, max_partition_size=mps, hypercube_families=fams)
+
+
+def test_edge_case_box_without_any_surface(ib, oracle):
+    """No immersed surface at all: only the hypercube family has ghosts; two separate families on opposite faces."""
+    fams = [("inlet", [(0, False)]), ("rest", [(0, True), (1, False), (1, True)])]
+    c = _AdHoc(ib, oracle, [0.0, 0.0], [1.0, 1.0], lambda m: (), lambda m: [(m.Ball([0.3, 0.6], 0.2), F32(0.02))], fams, mps=2_000)
+    assert len(c.dom.partitions) > 1 and sorted(c.dom.boundaries) == ["inlet", "rest"]
+    _check_tables(c)
+
+
+def test_edge_case_block_size_4(ib, oracle):
+    """4^2 blocks on a square root box (every width a power of two): all tables as the oracle's."""
+    seg = lambda m: (("plate", m.Stereolitography(np.array([[0.25, 0.25], [0.75, 0.25]], dtype=np.float64)), F32(0.02)),)
+    fams = [("far", [(0, False), (0, True), (1, False), (1, True)])]
+    c = _AdHoc(ib, oracle, [0.0, 0.0], [1.0, 1.0], seg, lambda m: [], fams, block_size=4)
+    assert c.msh.block_size == 4 and len(c.dom.boundaries["plate"]) >= 1
+    _check_tables(c)
+
+
+def test_edge_case_inexact_widths_corner_contacts(ib, oracle):
+    """A 2 : 1 root box splits 3 x 2 (src/mesher.jl:830-846): cell widths 2/3 / 2^k are not representable, and the
+    reference's float face test (src/ImmersedBoundary.jl:83-118: tolerance = 1 % of the LARGEST overlap) then admits
+    corner contacts whose 'overlap' is pure rounding noise -- the oracle, which restates that test over every candidate
+    pair, lists them.  The product lists the geometric faces only.  Pinned
+    here: same blocks and cells; the product's faces are a subset of the oracle's; every extra face of the oracle is a
+    corner contact (both overlaps below 1e-4 of a cell width); ghost sets agree."""
+    seg = lambda m: (("plate", m.Stereolitography(np.array([[0.5, 0.25], [1.5, 0.25]], dtype=np.float64)), F32(0.02)),)
+    fams = [("far", [(0, False), (0, True), (1, False), (1, True)])]
+    c = _AdHoc(ib, oracle, [0.0, 0.0], [2.0, 1.0], seg, lambda m: [], fams)
+    assert np.array_equal(c.msh.block_origins, c.omsh.block_origins) and np.array_equal(c.msh.block_widths, c.omsh.block_widths)
+    cen, wid = c.dom.cells()
+    assert np.array_equal(cen, c.odom.centers) and np.array_equal(wid, c.odom.widths)
+    mine, theirs = set(map(tuple, c.dom.faces().tolist())), set(map(tuple, np.asarray(c.odom.faces).tolist()))
+    assert mine <= theirs and len(theirs - mine) > 0
+    for d, i, j in theirs - mine:
+        lo = np.maximum(cen[i] - wid[i] / 2, cen[j] - wid[j] / 2)
+        hi = np.minimum(cen[i] + wid[i] / 2, cen[j] + wid[j] / 2)
+        assert i >= 0 and j >= 0 and (np.abs(hi - lo) < 1e-4 * wid[i]).all(), (d, i, j, hi - lo)
+    for name, obs in c.odom.boundaries.items():
+        for k, ob in obs.items():
+            assert np.array_equal(c.dom.boundaries[name][k].ghost_indices, ob.ghost_indices)
+
+
+def test_edge_case_surface_outside_the_box_has_no_ghosts(ib, oracle):
+    """A surface that never comes near the mesh: its family exists with zero ghosts (src/ImmersedBoundary.jl:194-230 keeps
+    nothing), the tables of the other family are unaffected, and the chunk lists agree with the oracle."""
+    seg = lambda m: (("far_plate", m.Stereolitography(np.array([[5.0, 5.0], [6.0, 5.0]], dtype=np.float64)), F32(0.05)),)
+    fams = [("box", [(0, False), (0, True), (1, False), (1, True)])]
+    c = _AdHoc(ib, oracle, [0.0, 0.0], [1.0, 1.0], seg, lambda m: [(m.Ball([0.5, 0.5], 0.2), F32(0.05))], fams)
+    assert sum(b.nghost for b in c.dom.boundaries["far_plate"].values()) == 0
+    _check_tables(c)
