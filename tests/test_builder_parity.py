@@ -195,3 +195,25 @@ def test_edge_case_surface_outside_the_box_has_no_ghosts(ib, oracle):
     c = _AdHoc(ib, oracle, [0.0, 0.0], [1.0, 1.0], seg, lambda m: [(m.Ball([0.5, 0.5], 0.2), F32(0.05))], fams)
     assert sum(b.nghost for b in c.dom.boundaries["far_plate"].values()) == 0
     _check_tables(c)
+
+
+@pytest.mark.parametrize("glr,skirt", [(F32(1.0), 1), (F32(2.25), 3)])
+def test_edge_case_ghost_layer_ratio_and_skirt_depth(ib, oracle, glr, skirt):
+    """Non-default `ghost_layer_ratio` / `partition_skirt_depth` (src/ImmersedBoundary.jl:536-537) on the 3-D STL sphere with
+    several partitions: thicker / thinner ghost bands (my block-level and projection prunings scale with the ratio) and
+    1- / 3-deep skirts."""
+    pts, tri = ib.synthetic.icosphere(1, 0.5)
+    M, OM = ib, oracle.mesher
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+    mk = lambda m: m.Mesh([-2, -2, -2], [4, 4, 4], ("wall", m.Stereolitography(pts, tri), F32(0.12)),
+                          refinement_regions=[(m.Ball([0, 0, 0], 0.9), F32(0.12))])
+
+    class Case:
+        pass
+
+    c = Case()
+    c.msh, c.omsh = mk(M), mk(OM)
+    c.dom = ib.Domain(c.msh, max_partition_size=20_000, partition_skirt_depth=skirt, ghost_layer_ratio=glr, hypercube_families=fams, upload=False)
+    c.odom = oracle.domain.Domain(c.omsh, max_partition_size=20_000, partition_skirt_depth=skirt, ghost_layer_ratio=glr, hypercube_families=fams)
+    assert len(c.dom.partitions) > 1
+    _check_tables(c)
