@@ -217,3 +217,19 @@ def test_edge_case_ghost_layer_ratio_and_skirt_depth(ib, oracle, glr, skirt):
     c.odom = oracle.domain.Domain(c.omsh, max_partition_size=20_000, partition_skirt_depth=skirt, ghost_layer_ratio=glr, hypercube_families=fams)
     assert len(c.dom.partitions) > 1
     _check_tables(c)
+
+
+def test_merge_points_of_several_surfaces(ib, oracle):
+    """`merge_points(stl1, stl2, ...)` (src/mesher.jl:351-407) with shared and duplicated vertices across the inputs: the
+    first point carrying a tag is kept, numbering in order of first appearance, degenerate simplices dropped -- the
+    product resolves the tags in parallel hash buckets, the result must be the sequential one."""
+    M, OM = ib, oracle.mesher
+    p1, t1 = ib.synthetic.icosphere(2, 0.5)
+    p2, t2 = ib.synthetic.icosphere(1, 0.5)                         # coarser sphere: vertices shared with p1 merge into p1's
+    p3 = p1[::-1].copy()                                            # the same points in another order ...
+    t3 = (len(p1) - 1 - t1)[:, [0, 0, 2]]                           # ... with only degenerate triangles
+    for tol in (1e-7, F32(1e-3)):
+        got = M.merge_points(M.Stereolitography(p1, t1), M.Stereolitography(p2, t2), M.Stereolitography(p3, t3), tolerance=tol)
+        ref = OM.merge_points(OM.Stereolitography(p1, t1), OM.Stereolitography(p2, t2), OM.Stereolitography(p3, t3), tolerance=tol)
+        assert np.array_equal(got.points, ref.points) and np.array_equal(got.simplices, ref.simplices)
+        assert len(got.points) <= len(p1) + len(p2) and len(got.simplices) == len(t1) + len(t2)
