@@ -233,3 +233,41 @@ def test_merge_points_of_several_surfaces(ib, oracle):
         ref = OM.merge_points(OM.Stereolitography(p1, t1), OM.Stereolitography(p2, t2), OM.Stereolitography(p3, t3), tolerance=tol)
         assert np.array_equal(got.points, ref.points) and np.array_equal(got.simplices, ref.simplices)
         assert len(got.points) <= len(p1) + len(p2) and len(got.simplices) == len(t1) + len(t2)
+
+
+def test_builder_tables_do_not_depend_on_the_thread_count(ib):
+    """The host builder runs its phases in parallel (STL refinement per simplex, hash-bucketed point merge, KD-tree halves
+    as tasks once a node holds more than 16 384 points, octree subtrees, ghost search per block) and restores the
+    sequential order afterwards.  The bench recipe two octree levels down (3.07 M cells, 5.9 M refined triangles -- large
+    enough for every parallel path) must give the same bytes with 1 thread and with all of them."""
+    import ctypes
+    import hashlib
+    import os
+    gomp = ctypes.CDLL("libgomp.so.1")
+    ncpu = os.cpu_count() or 2
+    pts, tri = ib.synthetic.icosphere(6, 0.5)
+    h = F32(32.0 / 2 ** 8 / 8 * 1.01)
+    fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
+
+    def digest(threads):
+        gomp.omp_set_num_threads(threads)
+        try:
+            m = ib.Mesh([-16, -16, -16], [32, 32, 32], ("wall", ib.Stereolitography(pts, tri), h), refinement_regions=[(ib.Ball([0, 0, 0], 0.75), h)])
+            dom = ib.Domain(m, max_partition_size=len(m), hypercube_families=fams, build_partitions=False, build_surfaces=False, upload=False)
+        finally:
+            gomp.omp_set_num_threads(ncpu)
+        H = hashlib.sha256()
+        c, w = dom.cells()
+        for a in (m.block_origins, m.block_widths, c, w, dom.block_faces()):
+            H.update(np.ascontiguousarray(a).tobytes())
+        n = 0
+        for chunks in dom.boundaries.values():
+            for b in chunks.values():
+                n += b.nghost
+                for f in ("ghost_indices", "image_domain", "projections", "normals_host", "image_distances", "ghost_distances", "interp_ptr", "interp_idx", "interp_w"):
+                    H.update(getattr(b, f).tobytes())
+        return len(m), n, H.hexdigest()
+
+    one, many = digest(1), digest(max(ncpu, 2))
+    assert one[0] == 3_072_000 and one[1] > 90_000
+    assert one == many
