@@ -717,16 +717,23 @@ std::shared_ptr<ibx_stl> refine_to_length_impl(const ibx_stl& s, Num h, double t
     // every input simplex refines on its own: chunks in parallel, outputs concatenated in input order
     const int64_t ns = s.nsimp(), CH = 64, nch = (ns + CH - 1) / CH;
     std::vector<std::vector<T>> outs((size_t)nch);
+    std::string err;   // an exception must not leave the parallel region
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t c = 0; c < nch; ++c) {
       std::vector<T>& out = outs[(size_t)c];
-      for (int64_t i = c * CH; i < std::min(ns, (c + 1) * CH); ++i) {
-        std::vector<T> simp((size_t)nd * nd);
-        for (int v = 0; v < nd; ++v)
-          for (int d = 0; d < nd; ++d) simp[v * nd + d] = (T)s.points[s.simplices[i * nd + v] * nd + d];
-        refine_simplex<T>(std::move(simp), nd, h, gm1, nreg, regs, out);
+      try {
+        for (int64_t i = c * CH; i < std::min(ns, (c + 1) * CH); ++i) {
+          std::vector<T> simp((size_t)nd * nd);
+          for (int v = 0; v < nd; ++v)
+            for (int d = 0; d < nd; ++d) simp[v * nd + d] = (T)s.points[s.simplices[i * nd + v] * nd + d];
+          refine_simplex<T>(std::move(simp), nd, h, gm1, nreg, regs, out);
+        }
+      } catch (const std::exception& e) {
+#pragma omp critical
+        err = e.what();
       }
     }
+    if (!err.empty()) throw std::runtime_error(err);
     size_t total = 0;
     for (auto& o : outs) total += o.size();
     tmp.points.reserve(total);
