@@ -271,3 +271,38 @@ def test_builder_tables_do_not_depend_on_the_thread_count(ib):
     one, many = digest(1), digest(max(ncpu, 2))
     assert one[0] == 3_072_000 and one[1] > 90_000
     assert one == many
+
+
+def test_edge_case_two_surfaces_regions_and_growth_ratio(ib, oracle):
+    """Two immersed surfaces with different sizes (refine_orderly, src/mesher.jl:878-918: the finer one is refined first and
+    becomes a refinement region of the coarser), `Box` and `Line` regions, a non-default growth ratio, Float64 geometry
+    next to Float32 sizes."""
+    fine = lambda m: m.Stereolitography(np.array([[0.2, 0.3], [0.45, 0.35], [0.6, 0.3]], dtype=np.float64))
+    coarse = lambda m: m.Stereolitography(np.array([[0.3, 0.7], [0.8, 0.75]], dtype=np.float64))
+    surfaces = lambda m: (("coarse", coarse(m), F32(0.04)), ("fine", fine(m), F32(0.01)))
+    regions = lambda m: [(m.Box([0.7, 0.1], [0.2, 0.15]), F32(0.02)), (m.Line([0.1, 0.9], [0.4, 0.95]), F32(0.03))]
+    fams = [("box", [(0, False), (0, True), (1, False), (1, True)])]
+    M, OM = ib, oracle.mesher
+
+    class Case:
+        pass
+
+    c = Case()
+    c.msh = M.Mesh([0.0, 0.0], [1.0, 1.0], *surfaces(M), refinement_regions=regions(M), growth_ratio=F32(1.6))
+    c.omsh = OM.Mesh([0.0, 0.0], [1.0, 1.0], *surfaces(OM), refinement_regions=regions(OM), growth_ratio=F32(1.6))
+    c.dom = ib.Domain(c.msh, max_partition_size=4_000, hypercube_families=fams, upload=False)
+    c.odom = oracle.domain.Domain(c.omsh, max_partition_size=4_000, hypercube_families=fams)
+    assert sorted(c.dom.boundaries) == ["box", "coarse", "fine"] and len(c.dom.partitions) > 1
+    _check_tables(c)
+
+
+def test_edge_case_3d_box_regions_block_size_4_no_surface(ib, oracle):
+    """3-D without a surface, 4^3 blocks, a `Box` region off-centre and a `Line` region: block lists, faces with 2:1
+    interfaces in all three directions, partitions, far-field ghosts."""
+    regions = lambda m: [(m.Box([0.1, 0.5, 0.2], [0.3, 0.2, 0.3]), F32(0.04)), (m.Line([0.8, 0.1, 0.1], [0.8, 0.9, 0.6]), F32(0.06))]
+    fams = [("x", [(0, False), (0, True)]), ("yz", [(1, False), (1, True), (2, False), (2, True)])]
+    c = _AdHoc(ib, oracle, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], lambda m: (), regions, fams, mps=6_000, block_size=4)
+    assert c.dom.ndims == 3 and len(c.dom.partitions) > 1
+    kinds = set(np.unique(c.dom.block_faces()[:, :, 0]).tolist())
+    assert {0, 1, 2, 3} <= kinds, kinds
+    _check_tables(c)
