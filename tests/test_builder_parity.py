@@ -306,3 +306,24 @@ def test_edge_case_3d_box_regions_block_size_4_no_surface(ib, oracle):
     kinds = set(np.unique(c.dom.block_faces()[:, :, 0]).tolist())
     assert {0, 1, 2, 3} <= kinds, kinds
     _check_tables(c)
+
+
+def test_surfaces_and_multigrid_3d_stl(get_case, ib, oracle):
+    """`Surface` of a 3-D STL wall (points, normals, areas, offsets, both interpolators; src/ImmersedBoundary.jl:743-763) and
+    the 8 -> 4 -> 2 multigrid hierarchy with its IDW transfer operators (:1355-1407) on the 3-D sphere mesh."""
+    c = get_case("sphere3d_stl", 20_000)
+    s, os_ = c.dom.surfaces["wall"], c.odom.surfaces["wall"]
+    assert s.points.shape[1] == 3 and np.array_equal(s.points, os_.points.astype(F32))
+    assert np.allclose(s.normals, os_.normals, atol=1e-6)
+    assert np.allclose(s.areas, os_.areas, rtol=1e-6) and np.allclose(s.offsets, os_.offsets, rtol=1e-6)
+    for (p, i, w), acc in (((s.ptr, s.idx, s.w), os_.interpolator), ((s.optr, s.oidx, s.ow), os_.offset_interpolator)):
+        optr, oidx, ow = acc.to_csr()
+        assert np.array_equal(p, optr) and np.array_equal(i, oidx) and np.abs(w - ow).max() < 5e-6
+    cd, pro, coa = ib.multigrid(c.dom)
+    ocd, opro, ocoa = oracle.domain.multigrid(c.odom)
+    assert [len(d) for d in cd] == [len(d) for d in ocd] and len(cd) >= 2
+    for a, b in zip(list(coa) + list(pro), list(ocoa) + list(opro)):
+        p, i, w = a.tables()
+        op, oi, ow = b.to_csr()
+        assert np.array_equal(p, op) and np.array_equal(i, oi) and np.abs(w - ow).max() < 1e-6
+    assert np.array_equal(cd[0].faces(), ocd[0].faces)
