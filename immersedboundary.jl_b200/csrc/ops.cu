@@ -414,8 +414,8 @@ __global__ void k_clamped_update(float* __restrict__ Q, const float* __restrict_
 }
 
 // one stage of a local-time-step march: Q = Q0 + ((alpha / cfl_i) * R) * mask_i, in that order of roundings
-__global__ void k_local_step(const float* __restrict__ Q0, const float* __restrict__ R, const float* __restrict__ cfl,
-                             const float* __restrict__ mask, float alpha, float* __restrict__ Q, int64_t n, int cols) {
+__global__ void k_local_step(const float* Q0, const float* __restrict__ R, const float* __restrict__ cfl,
+                             const float* __restrict__ mask, float alpha, float* Q, int64_t n, int cols) {   // Q may be Q0
   int64_t tot = n * cols;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot; t += (int64_t)gridDim.x * blockDim.x) {
     int64_t i = t % n;
