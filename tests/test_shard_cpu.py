@@ -10,10 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 F32 = np.float32
 
 
-def _build(ib):
+def _build(ib, for_rank=None):
     fams = [("farfield", [(d, s) for d in range(3) for s in (False, True)])]
     m = ib.Mesh([-2, -2, -2], [4, 4, 4], ("wall", ib.Sphere([0, 0, 0], 0.5), F32(0.12)),
                 refinement_regions=[(ib.Ball([0, 0, 0], 0.9), F32(0.24))])
+    if for_rank is not None:   # what bench.py does on every rank: ghosts searched in the rank's block range only
+        return m, fams, ib.Domain(m, max_partition_size=len(m), hypercube_families=fams, build_partitions=False, build_surfaces=False,
+                                  upload=False, for_rank=for_rank)
     return m, fams, ib.Domain(m, hypercube_families=fams, build_partitions=False, upload=False)
 
 
@@ -25,7 +28,7 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        _, _, g = _build(ib)
+        _, _, g = _build(ib, for_rank=(rank, world))
 
         def gather(obj):
             out = [None] * world
